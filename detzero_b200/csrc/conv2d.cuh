@@ -1,0 +1,10 @@
+// conv2d.cuh -- parameter block shared by the SIMT and tensor-core NHWC conv2d kernels
+#pragma once
+struct Conv2dParams {
+    const float* in; const float* w; const float* scale; const float* shift; float* out;
+    int B, H, W, cin, in_cstride;
+    int KH, KW, stride, pad;
+    int Ho, Wo, cout;
+    int OH, OW, os, oy0, ox0;        // physical output: pixel (ho*os+oy0, wo*os+ox0) of an (OH, OW) map
+    int out_coff, out_cstride, relu;
+};

@@ -1,0 +1,119 @@
+"""``CenterPoint`` detector template + module registry (the reference's "Detector3DTemplate" role):
+detection/detzero_det/models/centerpoint.py:15-129, models/__init__.py:8-29,
+centerpoint_modules/__init__.py:8-17.  Modules are looked up by NAME from the YAML config exactly like the reference;
+every module is ``forward(batch_dict) -> batch_dict``."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import backbone3d, dense, vfe
+
+#: module registry, same keys as detzero_det.models.centerpoint_modules.__all__ (PDVHead = 2nd stage, out of scope)
+cp_modules = {
+    'MeanVFE': vfe.MeanVFE,
+    'DynamicMeanVFE': vfe.DynamicMeanVFE,
+    'VoxelBackBone8x': backbone3d.VoxelBackBone8x,
+    'VoxelResBackBone8x': backbone3d.VoxelResBackBone8x,
+    'HeightCompression': dense.HeightCompression,
+    'BaseBEVBackbone': dense.BaseBEVBackbone,
+    'CenterHead': dense.CenterHead,
+}
+
+
+class CenterPoint(nn.Module):
+    def __init__(self, model_cfg, num_class, dataset):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.num_class = num_class
+        self.dataset = dataset
+        self.tta = getattr(dataset, 'tta', False)
+        self.class_names = dataset.class_names
+        self.register_buffer('global_step', torch.LongTensor(1).zero_())
+        self.second_stage = model_cfg.get('SECOND_STAGE', False)
+        if self.second_stage:
+            raise NotImplementedError('PDVHead second stage is out of scope (SURVEY.md §2.1)')
+        self.module_list = self.build_networks()
+
+    @property
+    def mode(self):
+        return 'TRAIN' if self.training else 'TEST'
+
+    def update_global_step(self):
+        self.global_step += 1
+
+    def build_networks(self):
+        ds = self.dataset
+        info = {'num_point_features': ds.point_feature_encoder.num_point_features, 'grid_size': ds.grid_size,
+                'point_cloud_range': ds.point_cloud_range, 'voxel_size': ds.voxel_size}
+        cfg = self.model_cfg
+        m_vfe = cp_modules[cfg.VFE.NAME](model_cfg=cfg.VFE, num_point_features=info['num_point_features'],
+                                         point_cloud_range=info['point_cloud_range'], voxel_size=info['voxel_size'],
+                                         grid_size=info['grid_size'],
+                                         max_points_per_voxel=getattr(ds, 'max_points_per_voxel', 5),
+                                         max_num_voxels=getattr(ds, 'max_num_voxels', 200000))
+        info['num_point_features'] = m_vfe.get_output_feature_dim()
+        m_b3d = cp_modules[cfg.BACKBONE_3D.NAME](model_cfg=cfg.BACKBONE_3D, input_channels=info['num_point_features'],
+                                                 grid_size=info['grid_size'], voxel_size=info['voxel_size'],
+                                                 point_cloud_range=info['point_cloud_range'])
+        info['num_point_features'] = m_b3d.num_point_features
+        m_bev = cp_modules[cfg.MAP_TO_BEV.NAME](model_cfg=cfg.MAP_TO_BEV, grid_size=info['grid_size'])
+        info['num_bev_features'] = m_bev.num_bev_features
+        m_b2d = cp_modules[cfg.BACKBONE_2D.NAME](model_cfg=cfg.BACKBONE_2D, input_channels=info['num_bev_features'])
+        info['num_bev_features'] = m_b2d.num_bev_features
+        m_head = cp_modules[cfg.DENSE_HEAD.NAME](
+            model_cfg=cfg.DENSE_HEAD, input_channels=info['num_bev_features'],
+            num_class=self.num_class if not cfg.DENSE_HEAD.CLASS_AGNOSTIC else 1, class_names=self.class_names,
+            grid_size=info['grid_size'], voxel_size=info['voxel_size'], point_cloud_range=info['point_cloud_range'],
+            tta=self.tta, predict_boxes_when_training=self.second_stage)
+        for name, m in (('vfe', m_vfe), ('backbone3d', m_b3d), ('map_to_bev', m_bev), ('backbone2d', m_b2d),
+                        ('dense_head', m_head)):
+            self.add_module(name, m)
+        return [m_vfe, m_b3d, m_bev, m_b2d, m_head]
+
+    def forward_device(self, batch_dict):
+        """all device work of one batch, no host sync (capturable in a CUDA graph); result =
+        batch_dict['final_boxes_padded'] (B,500,9) + ['final_boxes_count'] (B)"""
+        for m in self.module_list:
+            batch_dict = m(batch_dict)
+        return batch_dict
+
+    def forward(self, batch_dict):
+        if self.training:
+            raise NotImplementedError('training loop support is a next row (SURVEY.md §8f rank 1)')
+        batch_dict = self.forward_device(batch_dict)
+        return self.post_processing(batch_dict)
+
+    def post_processing(self, batch_dict):
+        """centerpoint.py:210-307 (single-stage branch): pred_dicts = final_box_dicts.  The recall bookkeeping
+        (generate_recall_record) needs gt boxes + 3D IoU and only feeds a log line; it is reported as empty.
+        This is the ONE device->host read of the step: box counts + per-level site counts (overflow check)."""
+        counts = batch_dict['final_boxes_count']
+        levels = [t for t in batch_dict.get('multi_scale_3d_features', {}).values()] + \
+                 [batch_dict.get('encoded_spconv_tensor')]
+        levels = [t for t in levels if t is not None and t._n is None]
+        flat = torch.cat([counts.flatten()] + [t._count for t in levels]).tolist()
+        nb = counts.numel()
+        for t, n in zip(levels, flat[nb:]):
+            if n > t._cap:
+                raise RuntimeError('sparse level overflow: %d sites > capacity %d' % (n, t._cap))
+            t._n = int(n)
+        shaped = torch.tensor(flat[:nb]).view(counts.shape)
+        pred_dicts = dense.CenterHead.boxes_to_dicts(batch_dict['final_boxes_padded'], shaped)
+        batch_dict['final_box_dicts'] = pred_dicts
+        return pred_dicts, {}
+
+
+def build_network(model_cfg, num_class, dataset):
+    return {'CenterPoint': CenterPoint}[model_cfg.NAME](model_cfg=model_cfg, num_class=num_class, dataset=dataset)
+
+
+def load_data_to_gpu(batch_dict, device='cuda'):
+    """models/__init__.py:21-29 -- every ndarray -> float CUDA tensor (non_blocking from pinned memory)"""
+    for key, val in batch_dict.items():
+        if key in ('frame_id', 'metadata', 'sequence_name', 'pose', 'tta_ops', 'aug_matrix_inv', 'points_per_frame'):
+            continue
+        if isinstance(val, np.ndarray):
+            batch_dict[key] = torch.from_numpy(val).float().to(device, non_blocking=True)
+        elif isinstance(val, torch.Tensor) and not val.is_cuda:
+            batch_dict[key] = val.float().to(device, non_blocking=True)
+    return batch_dict

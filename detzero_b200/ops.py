@@ -1,0 +1,273 @@
+"""torch-facing wrappers over the C ABI.  torch is plumbing only: device memory, the current stream.
+
+Every function enqueues on ``torch.cuda.current_stream()`` and never synchronises the host."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, farr, iarr, lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('detzero_b200 ops need CUDA tensors (no CPU fallback); got a %s tensor' % t.device)
+
+
+def _f32c(t):
+    assert t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.is_contiguous())
+    return t
+
+
+class GridIndex:
+    """bitmap + popcount prefix (+perm) over a (B, D, H, W) lattice; rank order == ascending (b,z,y,x)."""
+
+    def __init__(self, B, dhw, device, with_perm_cap=None):
+        self.B, self.dhw = int(B), [int(v) for v in dhw]
+        self.words = lib().dz_grid_index_words(self.B, *self.dhw)
+        self.bitmap = torch.zeros(self.words, dtype=torch.int32, device=device)
+        self.prefix = torch.empty(self.words, dtype=torch.int32, device=device)
+        self.perm = torch.empty(with_perm_cap, dtype=torch.int32, device=device) if with_perm_cap else None
+
+    def clear(self):
+        self.bitmap.zero_()
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag='ws'):
+    """a grow-only scratch buffer per (device, tag) -- stream-ordered reuse on the current stream"""
+    key = (str(device), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def scan_ws_bytes(words):
+    return lib().dz_scan_ws_bytes(words)
+
+
+def grid_index_from_coords(coords, d_n, cap, B, dhw, with_perm=True):
+    _need_cuda(coords)
+    gi = GridIndex(B, dhw, coords.device, with_perm_cap=cap if with_perm else None)
+    total = torch.zeros(1, dtype=torch.int32, device=coords.device)
+    ws = workspace(scan_ws_bytes(gi.words), coords.device)
+    check(lib().dz_grid_index_from_coords(_p(coords), _p(d_n), cap, gi.B, *gi.dhw, _p(gi.bitmap), _p(gi.prefix),
+                                          _p(gi.perm), _p(total), _p(ws), ws.numel(), _stream()), 'grid_index_from_coords')
+    return gi
+
+
+def voxelize_hard(points, xyz_off, c, pc_range, voxel_size, grid_zyx, max_pts, max_voxels, batch_idx,
+                  voxels, coords, num, mean, counters, index):
+    """one cloud -> rows appended at counters[0]; see include/detzero_b200.h dz_voxelize_hard"""
+    _need_cuda(points, voxels)
+    _f32c(points)
+    n, stride = points.shape
+    cap = voxels.shape[0]
+    nbytes = lib().dz_voxelize_hard_ws_bytes(n, max_pts, max_voxels, *index.dhw)
+    ws = workspace(nbytes, points.device)
+    check(lib().dz_voxelize_hard(_p(points), n, stride, xyz_off, c, farr(pc_range), farr(voxel_size), iarr(grid_zyx),
+                                 max_pts, max_voxels, batch_idx, _p(voxels), _p(coords), _p(num), _p(mean), cap,
+                                 _p(counters), index.B, *index.dhw, _p(index.bitmap), _p(index.prefix), _p(index.perm),
+                                 _p(ws), ws.numel(), _stream()), 'voxelize_hard')
+
+
+def mean_vfe(voxels, num_i32):
+    _need_cuda(voxels, num_i32)
+    m, p, c = voxels.shape
+    out = torch.empty((m, c), dtype=torch.float32, device=voxels.device)
+    check(lib().dz_mean_vfe(_p(_f32c(voxels)), _p(num_i32), m, p, c, _p(out), _stream()), 'mean_vfe')
+    return out
+
+
+def voxelize_dynamic_mean(points, c, B, pc_range, voxel_size, grid_xyz, cap):
+    _need_cuda(points)
+    _f32c(points)
+    n = points.shape[0]
+    assert points.shape[1] == 1 + c
+    feats = torch.empty((cap, c), dtype=torch.float32, device=points.device)
+    coords = torch.zeros((cap, 4), dtype=torch.int32, device=points.device)
+    d_m = torch.zeros(1, dtype=torch.int32, device=points.device)
+    nbytes = lib().dz_voxelize_dynamic_ws_bytes(n, cap, B, *[int(g) for g in grid_xyz])
+    ws = workspace(nbytes, points.device, 'dyn')
+    check(lib().dz_voxelize_dynamic_mean(_p(points), n, c, B, farr(pc_range), farr(voxel_size), iarr(grid_xyz),
+                                         _p(feats), _p(coords), cap, _p(d_m), _p(ws), ws.numel(), _stream()),
+          'voxelize_dynamic_mean')
+    return feats, coords, d_m
+
+
+def rulebook_subm(coords, d_n, cap, index, ksize):
+    K = ksize[0] * ksize[1] * ksize[2]
+    nbr = torch.empty((K, cap), dtype=torch.int32, device=coords.device)
+    check(lib().dz_rulebook_subm(_p(coords), _p(d_n), cap, index.B, *index.dhw, iarr(ksize), _p(index.bitmap),
+                                 _p(index.prefix), _p(index.perm), _p(nbr), _stream()), 'rulebook_subm')
+    return nbr
+
+
+def conv_out_dhw(in_dhw, ksize, stride, pad):
+    return [(in_dhw[d] + 2 * pad[d] - (ksize[d] - 1) - 1) // stride[d] + 1 for d in range(3)]
+
+
+def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap):
+    dev = coords.device
+    out_dhw = conv_out_dhw(in_index.dhw, ksize, stride, pad)
+    out_index = GridIndex(in_index.B, out_dhw, dev)
+    K = ksize[0] * ksize[1] * ksize[2]
+    out_coords = torch.zeros((out_cap, 4), dtype=torch.int32, device=dev)
+    d_n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbr = torch.empty((K, out_cap), dtype=torch.int32, device=dev)
+    ws = workspace(scan_ws_bytes(out_index.words), dev)
+    check(lib().dz_rulebook_conv(_p(coords), _p(d_n), in_cap, in_index.B, iarr(in_index.dhw), iarr(ksize), iarr(stride),
+                                 iarr(pad), _p(in_index.bitmap), _p(in_index.prefix), _p(in_index.perm), _p(out_coords),
+                                 _p(d_n_out), out_cap, _p(out_index.bitmap), _p(out_index.prefix), _p(nbr), _p(ws),
+                                 ws.numel(), _stream()), 'rulebook_conv')
+    return out_coords, d_n_out, out_index, nbr, out_dhw
+
+
+def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None):
+    """feats (in_cap, cin); nbr (K, nbr_cap); weight_packed (K, cin, cout)"""
+    _need_cuda(feats, nbr, weight_packed)
+    K, cin, cout = weight_packed.shape
+    assert feats.shape[1] == cin and nbr.shape[0] == K
+    if out is None:
+        out = torch.empty((out_cap, cout), dtype=torch.float32, device=feats.device)
+    check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, _p(nbr), K, nbr.shape[1], _p(d_n_out), out_cap,
+                              _p(_f32c(weight_packed)), _p(scale), _p(shift), _p(residual), int(relu), _p(out), cout,
+                              mode, _stream()), 'spconv_fwd')
+    return out
+
+
+def sparse_to_bev(feats, coords, d_n, cap, B, D, H, W, out=None):
+    c = feats.shape[1]
+    if out is None:
+        out = torch.zeros((B, H, W, c * D), dtype=torch.float32, device=feats.device)
+    else:
+        out.zero_()
+    check(lib().dz_sparse_to_bev(_p(_f32c(feats)), _p(coords), _p(d_n), cap, c, B, D, H, W, _p(out), _stream()),
+          'sparse_to_bev')
+    return out
+
+
+def conv2d(x, weight_packed, stride, pad, scale, shift, relu, out=None, out_coff=0, mode=_lib.DZ_F32):
+    """x (B,H,W,cin) NHWC (may be a channel-slice view's base with in_cstride); weight (KH,KW,cin,cout)"""
+    _need_cuda(x, weight_packed)
+    B, H, W, cstride = x.shape
+    KH, KW, cin, cout = weight_packed.shape
+    assert cin == cstride
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x.device)
+    assert out.shape[:3] == (B, Ho, Wo)
+    check(lib().dz_conv2d_fwd(_p(_f32c(x)), B, H, W, cin, cstride, _p(_f32c(weight_packed)), KH, KW, stride, pad,
+                              _p(scale), _p(shift), int(relu), _p(out), Ho, Wo, cout, out_coff, out.shape[3], mode,
+                              _stream()), 'conv2d_fwd')
+    return out
+
+
+def deconv2d(x, weight_packed, scale, shift, relu, out=None, out_coff=0, mode=_lib.DZ_F32):
+    """ConvTranspose2d with kernel == stride; weight (s,s,cin,cout)"""
+    B, H, W, cin = x.shape
+    s, s2, cin2, cout = weight_packed.shape
+    assert s == s2 and cin2 == cin
+    if out is None:
+        out = torch.empty((B, H * s, W * s, cout), dtype=torch.float32, device=x.device)
+    check(lib().dz_deconv2d_fwd(_p(_f32c(x)), B, H, W, cin, _p(_f32c(weight_packed)), s, _p(scale), _p(shift),
+                                int(relu), _p(out), cout, out_coff, out.shape[3], mode, _stream()), 'deconv2d_fwd')
+    return out
+
+
+def centerhead_decode(head, ch_layout, num_class, K, pc_range, voxel_size, fmap_stride, post_limit, score_thresh,
+                      use_iou):
+    """head (B,H,W,ch) NHWC; ch_layout dict of channel offsets: center, center_z, dim, rot, iou, hm"""
+    B, H, W, ch = head.shape
+    dev = head.device
+    boxes = torch.zeros((B, K, 7), dtype=torch.float32, device=dev)
+    scores = torch.zeros((B, K), dtype=torch.float32, device=dev)
+    labels = torch.zeros((B, K), dtype=torch.int32, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    nbytes = lib().dz_centerhead_decode_ws_bytes(B, H, W, num_class, K)
+    ws = workspace(nbytes, dev, 'decode')
+    check(lib().dz_centerhead_decode(_p(_f32c(head)), B, H, W, ch, ch_layout['center'], ch_layout['center_z'],
+                                     ch_layout['dim'], ch_layout['rot'], ch_layout.get('iou', 0), ch_layout['hm'],
+                                     num_class, K, farr(pc_range), farr(voxel_size), int(fmap_stride), farr(post_limit),
+                                     float(score_thresh), int(use_iou), _p(boxes), _p(scores), _p(labels), _p(d_n),
+                                     _p(ws), ws.numel(), _stream()), 'centerhead_decode')
+    return boxes, scores, labels, d_n
+
+
+def nms_bev(boxes, scores, labels, d_n, thresh, post_max, label_offset=1):
+    """boxes (B,cap,7) in descending score order; returns out (B,post_max,9), d_out_n (B)"""
+    B, cap, _ = boxes.shape
+    dev = boxes.device
+    out = torch.empty((B, post_max, 9), dtype=torch.float32, device=dev)
+    d_out_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    ws = workspace(lib().dz_nms_bev_ws_bytes(B, cap), dev, 'nms')
+    check(lib().dz_nms_bev(_p(_f32c(boxes)), _p(_f32c(scores)), _p(labels), _p(d_n), B, cap, float(thresh), post_max,
+                           label_offset, _p(out), _p(d_out_n), _p(ws), ws.numel(), _stream()), 'nms_bev')
+    return out, d_out_n
+
+
+def boxes_iou_bev(a, b):
+    _need_cuda(a, b)
+    a = a[:, :7].contiguous().float()
+    b = b[:, :7].contiguous().float()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    check(lib().dz_boxes_iou_bev(_p(a), a.shape[0], _p(b), b.shape[0], _p(out), _stream()), 'boxes_iou_bev')
+    return out
+
+
+def linear(x, w, scale=None, shift=None, relu=False, out=None, mode=_lib.DZ_F32):
+    """y = act((x @ w.T) * scale + shift); x (M,K), w (N,K)"""
+    _need_cuda(x, w)
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    ldy = out.stride(0)
+    check(lib().dz_linear_fwd(_p(_f32c(x)), M, K, _p(_f32c(w)), N, _p(scale), _p(shift), int(relu), _p(out), ldy, mode,
+                              _stream()), 'linear_fwd')
+    return out
+
+
+def group_max(x, G, group):
+    C = x.shape[1]
+    assert x.shape[0] == G * group
+    y = torch.empty((G, C), dtype=torch.float32, device=x.device)
+    check(lib().dz_group_max(_p(_f32c(x)), G, group, C, _p(y), _stream()), 'group_max')
+    return y
+
+
+def attention(q, k, v, key_padding_mask, H, mode=_lib.DZ_F32):
+    """q (B,Pq,E) pre-scaled, k/v (B,Pk,E) -- may be strided views with contiguous last dim; mask (B,Pk) uint8"""
+    _need_cuda(q, k, v)
+    B, Pq, E = q.shape
+    Pk = k.shape[1]
+    dh = E // H
+    for t in (q, k, v):
+        assert t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    out = torch.empty((B, Pq, E), dtype=torch.float32, device=q.device)
+    check(lib().dz_attention_fwd(_p(q), q.stride(1), _p(k), k.stride(1), _p(v), v.stride(1), _p(key_padding_mask), B, Pq,
+                                 Pk, H, dh, _p(out), E, mode, _stream()), 'attention_fwd')
+    return out
+
+
+def layernorm_residual(x, r, gamma, beta, eps=1e-5):
+    M, C = x.shape
+    y = torch.empty_like(x)
+    check(lib().dz_layernorm_residual(_p(_f32c(x)), _p(r), _p(gamma), _p(beta), float(eps), M, C, _p(y), _stream()),
+          'layernorm_residual')
+    return y

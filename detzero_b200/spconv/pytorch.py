@@ -1,0 +1,262 @@
+"""``spconv.pytorch``-shaped API on top of libdetzero_b200 (sm_100a).
+
+Mirrors exactly the surface the reference touches: ``SparseConvTensor(features=, indices=,
+spatial_shape=, batch_size=)`` with ``.features .indices .spatial_shape .batch_size .indice_dict
+.replace_feature() .dense()``; ``SubMConv3d`` / ``SparseConv3d(in, out, k, stride=, padding=, bias=, indice_key=)``
+with spconv-2.x weight layout ``(Cout, KD, KH, KW, Cin)`` (state-dict compatible);
+``SparseSequential``; ``SparseModule``; ``SparseInverseConv3d`` (never constructed by the shipped configs).
+Reference call sites: detection/detzero_det/models/centerpoint_modules/backbone3d.py:68-73,93-100,135-195.
+
+B200-native differences (behaviour-preserving):
+  * tensors carry a *capacity* and a device-side row count, so a whole backbone runs without a host sync;
+    ``.features`` / ``.indices`` slice to the true row count lazily (one D2H only if the caller asks)
+  * the rulebook is a neighbour table built from an L2-resident grid index (no hash table, no sort);
+    strided-conv output sites are emitted sorted by (b,z,y,x) (spconv's order is implementation-defined)
+  * in eval mode ``SparseSequential`` fuses conv + BatchNorm1d + ReLU (+ residual) into one launch.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+class SparseConvTensor:
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None,
+                 benchmark=False, *, count=None, n_host=None, index=None):
+        if not features.is_cuda:
+            raise RuntimeError('detzero_b200.spconv needs CUDA tensors (there is no CPU fallback)')
+        self._feat = features
+        self._idx = indices if indices.dtype == torch.int32 else indices.int()
+        if not self._idx.is_contiguous():
+            self._idx = self._idx.contiguous()
+        self.spatial_shape = [int(s) for s in spatial_shape]
+        self.batch_size = int(batch_size)
+        self.indice_dict = indice_dict if indice_dict is not None else {}
+        self._cap = int(features.shape[0])
+        if count is None:
+            n_host = self._cap
+            count = torch.full((1,), self._cap, dtype=torch.int32, device=features.device)
+        self._count = count
+        self._n = n_host
+        self._index = index
+
+    # ---- spconv-visible surface ---------------------------------------------------------------------------
+    def num(self):
+        """true number of rows (host int); one device->host read the first time if it is not known yet"""
+        if self._n is None:
+            n = int(self._count.item())
+            if n > self._cap:
+                raise RuntimeError('sparse tensor overflow: %d sites > capacity %d (raise the capacity factor)' % (n, self._cap))
+            self._n = n
+        return self._n
+
+    @property
+    def features(self):
+        return self._feat[:self.num()]
+
+    @features.setter
+    def features(self, v):          # spconv 1.x style assignment (backbone3d.py:59-62 else-branch)
+        self._feat = v
+
+    @property
+    def indices(self):
+        return self._idx[:self.num()]
+
+    def replace_feature(self, new_features):
+        t = SparseConvTensor.__new__(SparseConvTensor)
+        t.__dict__.update(self.__dict__)
+        if new_features.shape[0] != self._cap:               # caller sliced to the true size
+            t._cap = int(new_features.shape[0])
+            t._idx = self._idx[:t._cap]
+            t._n = t._cap
+            t._count = torch.full((1,), t._cap, dtype=torch.int32, device=new_features.device)
+        t._feat = new_features
+        return t
+
+    def dense(self, channels_first=True):
+        """(B, C, D, H, W) like spconv's .dense() (height_compression.py:21)"""
+        D, H, W = self.spatial_shape
+        c = self._feat.shape[1]
+        nhwc = ops.sparse_to_bev(self._feat, self._idx, self._count, self._cap, self.batch_size, D, H, W)  # (B,H,W,c*D)
+        x = nhwc.view(self.batch_size, H, W, c, D)
+        return x.permute(0, 3, 4, 1, 2).contiguous() if channels_first else x
+
+    # ---- internal ------------------------------------------------------------------------------------------
+    def grid_index(self):
+        if self._index is None:
+            self._index = ops.grid_index_from_coords(self._idx, self._count, self._cap, self.batch_size,
+                                                     self.spatial_shape, with_perm=True)
+        return self._index
+
+    def _like(self, feat):
+        t = SparseConvTensor.__new__(SparseConvTensor)
+        t.__dict__.update(self.__dict__)
+        t._feat = feat
+        return t
+
+
+class SparseModule(nn.Module):
+    pass
+
+
+_fold_cache = {}
+
+
+def fold_bn(bn, conv_bias, device=None):
+    """eval-mode BatchNorm folded to (scale, shift): y = conv*scale + shift.  Cached per module; refreshed when any
+    involved tensor is modified in place (load_state_dict bumps ``_version``)."""
+    ts = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, conv_bias) if t is not None]
+    ver = tuple((t._version, t.data_ptr()) for t in ts)
+    hit = _fold_cache.get(id(bn))
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        scale = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        if bn.affine:
+            scale = scale * bn.weight.detach().float()
+        shift = -bn.running_mean.detach().float() * scale
+        if bn.affine:
+            shift = shift + bn.bias.detach().float()
+        if conv_bias is not None:
+            shift = shift + conv_bias.detach().float() * scale
+        scale, shift = scale.contiguous(), shift.contiguous()
+    _fold_cache[id(bn)] = (ver, scale, shift)
+    return scale, shift
+
+
+class _RuleSubm:
+    def __init__(self, nbr):
+        self.nbr = nbr
+
+
+class _RuleConv:
+    def __init__(self, out_idx, d_n_out, out_index, nbr, out_dhw, out_cap):
+        self.out_idx, self.d_n_out, self.out_index, self.nbr, self.out_dhw, self.out_cap = \
+            out_idx, d_n_out, out_index, nbr, out_dhw, out_cap
+
+
+class _SparseConv(SparseModule):
+    #: capacity of a strided conv's output relative to its input capacity (k3 s2 sites grow by <= ~1.5x in practice,
+    #: 8x in theory); overflow is detected (device count > capacity) and raised, never silently truncated
+    OUT_CAP_FACTOR = 3.0
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, subm=False, algo=None, mode='fp32'):
+        super().__init__()
+        assert groups == 1 and _triple(dilation) == [1, 1, 1], 'only what backbone3d.py uses'
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
+        self.kernel_size, self.stride, self.padding = _triple(kernel_size), _triple(stride), _triple(padding)
+        self.subm = subm
+        self.indice_key = indice_key
+        self.mode = mode
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        self._packed = None
+        self._packed_ver = None
+
+    def packed_weight(self):
+        """(K, Cin, Cout) contiguous copy of the spconv-layout parameter (refreshed when the parameter changes)"""
+        ver = (self.weight._version, self.weight.data_ptr())
+        if self._packed is None or self._packed_ver != ver:
+            w = self.weight.detach()
+            self._packed = w.reshape(self.out_channels, -1, self.in_channels).permute(1, 2, 0).contiguous().float()
+            self._packed_ver = ver
+        return self._packed
+
+    def _rule(self, x):
+        key = self.indice_key
+        rule = x.indice_dict.get(key) if key is not None else None
+        if rule is None:
+            if self.subm:
+                rule = _RuleSubm(ops.rulebook_subm(x._idx, x._count, x._cap, x.grid_index(), self.kernel_size))
+            else:
+                in_index = x.grid_index()
+                out_dhw = ops.conv_out_dhw(x.spatial_shape, self.kernel_size, self.stride, self.padding)
+                cells = x.batch_size * out_dhw[0] * out_dhw[1] * out_dhw[2]
+                grow = self.OUT_CAP_FACTOR if max(self.stride) > 1 and min(self.kernel_size) > 1 else 1.0
+                out_cap = int(min(cells, max(64, int(x._cap * grow))))
+                rule = _RuleConv(*_reorder(ops.rulebook_conv(x._idx, x._count, x._cap, in_index, self.kernel_size,
+                                                              self.stride, self.padding, out_cap)), out_cap)
+            if key is not None:
+                x.indice_dict[key] = rule
+        return rule
+
+    def forward_fused(self, x, scale=None, shift=None, residual=None, relu=False):
+        rule = self._rule(x)
+        mode = _lib.MODES[self.mode]
+        if self.subm:
+            out = ops.spconv_fwd(x._feat, rule.nbr, x._count, x._cap, self.packed_weight(), scale, shift,
+                                 None if residual is None else residual._feat, relu, mode)
+            return x._like(out)
+        out = ops.spconv_fwd(x._feat, rule.nbr, rule.d_n_out, rule.out_cap, self.packed_weight(), scale, shift, None,
+                             relu, mode)
+        return SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
+                                count=rule.d_n_out, n_host=None, index=rule.out_index)
+
+    def forward(self, x):
+        shift = None if self.bias is None else self.bias.detach().float()
+        return self.forward_fused(x, None, shift, None, False)
+
+
+def _reorder(t):
+    out_coords, d_n_out, out_index, nbr, out_dhw = t
+    return out_coords, d_n_out, out_index, nbr, out_dhw
+
+
+class SubMConv3d(_SparseConv):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, **kw):
+        super().__init__(in_channels, out_channels, kernel_size, 1, padding, dilation, groups, bias, indice_key, True,
+                         algo, kw.get('mode', 'fp32'))
+
+
+class SparseConv3d(_SparseConv):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, **kw):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, indice_key,
+                         False, algo, kw.get('mode', 'fp32'))
+
+
+class SparseInverseConv3d(SparseModule):
+    def __init__(self, *a, **kw):
+        super().__init__()
+        raise NotImplementedError('SparseInverseConv3d is never constructed by the shipped configs '
+                                  '(backbone3d.py:72-73); listed as a next row in SURVEY.md §8f')
+
+
+class SparseSequential(SparseModule):
+    """Applies SparseModules to the tensor and plain nn.Modules to ``.features`` (spconv semantics).  In eval mode
+    the pattern conv -> BatchNorm1d [-> ReLU] is executed as ONE fused launch."""
+
+    def __init__(self, *mods):
+        super().__init__()
+        for i, m in enumerate(mods):
+            self.add_module(str(i), m)
+
+    def forward(self, x):
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, _SparseConv) and not self.training and i + 1 < len(mods) and \
+                    isinstance(mods[i + 1], nn.BatchNorm1d) and not mods[i + 1].training:
+                bn = mods[i + 1]
+                relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                scale, shift = fold_bn(bn, m.bias, x._feat.device)
+                x = m.forward_fused(x, scale, shift, None, relu)
+                i += 3 if relu else 2
+            elif isinstance(m, SparseModule):
+                x = m(x)
+                i += 1
+            else:
+                x = x._like(m(x._feat))        # acts on all capacity rows; rows beyond the count are never read
+                i += 1
+        return x

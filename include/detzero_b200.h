@@ -1,0 +1,173 @@
+/*
+ * detzero_b200.h -- C ABI of libdetzero_b200.so (sm_100a).
+ *
+ * The reference (PJLab-ADG/DetZero) has no C ABI: its native ops are pybind11 modules taking at::Tensor
+ * (utils/detzero_utils/ops/iou3d_nms/src/iou3d_nms_api.cpp:10-17) and its sparse-conv / voxelizer arithmetic
+ * lives in the third-party spconv wheel.  Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked "host"; the caller owns all buffers incl. workspace
+ *   - functions only enqueue work on `stream` (a cudaStream_t): no malloc, no sync, no host loop
+ *   - element counts that are only known on the device are passed as `const int* d_n` (device scalar) together
+ *     with a host-side capacity `cap`; kernels are persistent / grid-stride over `cap` and read `*d_n`
+ *   - return 0 on success, <0 on error (never exit(); contrast iou3d_nms.cpp:14-26); dz_last_error_string()
+ *   - feature tensors are row-major (rows, channels); dense maps are NHWC
+ *
+ * Grid index ("coordinate index"): for a lattice (B, D, H, W) a bitmap of occupied cells + an exclusive
+ * popcount prefix per 32-bit word (+ optional permutation rank->row).  cell = b*cells_pad + (z*H+y)*W+x with
+ * cells_pad = round_up(D*H*W, 32).  Rank order == ascending (b,z,y,x).
+ */
+#ifndef DETZERO_B200_H
+#define DETZERO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dz_stream_t;           /* cudaStream_t */
+
+enum { DZ_OK = 0, DZ_ERR_ARG = -1, DZ_ERR_CUDA = -2, DZ_ERR_WORKSPACE = -3, DZ_ERR_UNSUPPORTED = -4 };
+enum { DZ_F32 = 0, DZ_TF32 = 1, DZ_BF16 = 2 };   /* arithmetic mode of GEMM-shaped kernels */
+
+int         dz_version(void);
+int         dz_sm_arch(void);                      /* 100 : built for sm_100a */
+const char* dz_last_error_string(void);            /* host string, thread-local */
+
+/* ---- grid index ---------------------------------------------------------------------------------------- */
+size_t dz_grid_index_words(int B, int D, int H, int W);          /* number of u32 words in bitmap == prefix */
+size_t dz_scan_ws_bytes(size_t n_words);
+/* prefix[w] = base + popcount(bitmap[0..w)), *d_total = base + popcount(all); base = d_base ? *d_base : 0 */
+int dz_grid_index_scan(const uint32_t* bitmap, uint32_t* prefix, size_t n_words, const int* d_base,
+                       int* d_total, void* ws, size_t ws_bytes, dz_stream_t stream);
+/* arbitrary site list -> index (+perm: rank -> row).  Replaces the hash table spconv builds inside
+ * SparseConvTensor/indice_dict (backbone3d.py:190-195).  bitmap must be zero on entry. */
+int dz_grid_index_from_coords(const int32_t* coords, const int* d_n, int cap, int B, int D, int H, int W,
+                              uint32_t* bitmap, uint32_t* prefix, int32_t* perm, int* d_total,
+                              void* ws, size_t ws_bytes, dz_stream_t stream);
+
+/* ---- voxelization -------------------------------------------------------------------------------------- */
+/* Hard voxelization of ONE cloud, order-exact with spconv.utils.Point2VoxelCPU3d.point_to_voxel as driven by
+ * detection/detzero_det/datasets/processor/data_processor.py:61-91 (first-appearance voxel ids, first max_pts
+ * points kept in input order, voxel cap in appearance order), fused with MeanVFE.forward (vfe.py:66-83).
+ *   points (n, point_stride) f32; the c feature columns [xyz_off, xyz_off+c) start with x,y,z and are copied
+ *   verbatim (xyz_off = 1 for a collated (N,1+C) [b,x,y,z,..] tensor, 0 for a raw (N,C) cloud)
+ *   voxels (cap, max_pts, c) ; coords (cap,4) [batch_idx,z,y,x] ; num_per_voxel (cap) ; mean (cap,c) or NULL
+ *   d_counters[0] = rows already used in voxels/coords (in/out), d_counters[1] = ranks already used in the
+ *   index (in/out): calling once per frame with batch_idx = 0..B-1 on one stream builds a collated batch
+ *   (dataset.py:260-303) without a host sync.
+ *   index_* : level-0 grid index over lattice (B, iD, iH, iW) (iD = sparse_shape z = grid z + 1,
+ *   backbone3d.py:133); bitmap must be zero before the first frame of a batch. */
+size_t dz_voxelize_hard_ws_bytes(int n_points, int max_pts, int max_voxels, int iD, int iH, int iW);
+int dz_voxelize_hard(const float* points, int n, int point_stride, int xyz_off, int c,
+                     const float* range_xyz6_host, const float* vsize_xyz3_host, const int* grid_zyx3_host,
+                     int max_pts, int max_voxels, int batch_idx,
+                     float* voxels, int32_t* coords, int32_t* num_per_voxel, float* mean, int cap,
+                     int* d_counters,
+                     int B, int iD, int iH, int iW, uint32_t* index_bitmap, uint32_t* index_prefix,
+                     int32_t* index_perm,
+                     void* ws, size_t ws_bytes, dz_stream_t stream);
+
+/* MeanVFE.forward (vfe.py:66-83) on an already voxelized batch: out (M,C) = voxels.sum(1) / max(num,1) */
+int dz_mean_vfe(const float* voxels, const int32_t* num_per_voxel, int M, int P, int C, float* out,
+                dz_stream_t stream);
+
+/* Dynamic mean voxelization of a collated batch: DynamicMeanVFE.forward (vfe.py:110-147): floor((p-lo)/vs),
+ * in-range mask, key b*XYZ + x*YZ + y*Z + z, unique (sorted), scatter_mean of all c columns.
+ *   points (n, 1+c) [b,x,y,z,...] ; out feats (cap,c), coords (cap,4) [b,z,y,x] ordered by ascending key ;
+ *   *d_m = number of voxels.  bitmap_xyz: B*round_up(X*Y*Z,32)/32 words, zero on entry. */
+size_t dz_voxelize_dynamic_ws_bytes(int n_points, int cap, int B, int X, int Y, int Z);
+int dz_voxelize_dynamic_mean(const float* points, int n, int c, int B,
+                             const float* range_xyz6_host, const float* vsize_xyz3_host,
+                             const int* grid_xyz3_host, float* feats, int32_t* coords, int cap, int* d_m,
+                             void* ws, size_t ws_bytes, dz_stream_t stream);
+
+/* ---- rulebook ------------------------------------------------------------------------------------------ */
+/* Neighbour table form of the spconv rulebook: nbr[k*cap + o] = input row feeding output row o through kernel
+ * offset k = (kz*KH+ky)*KW+kx, or -1.  The pair set {(k, nbr, o)} equals spconv's indice pairs
+ * (SubMConv3d: backbone3d.py:68,93-100,136 ; SparseConv3d: :70-71,169-170,183-184). */
+int dz_rulebook_subm(const int32_t* coords, const int* d_n, int cap, int B, int D, int H, int W,
+                     const int* ksize3_host, const uint32_t* bitmap, const uint32_t* prefix,
+                     const int32_t* perm, int32_t* nbr, dz_stream_t stream);
+/* Strided conv: generates the output site set (sorted ascending (b,z,y,x)), its grid index and the table.
+ * out_bitmap must be zero on entry. */
+int dz_rulebook_conv(const int32_t* in_coords, const int* d_n_in, int in_cap, int B,
+                     const int* in_dhw3_host, const int* ksize3_host, const int* stride3_host,
+                     const int* pad3_host, const uint32_t* in_bitmap, const uint32_t* in_prefix,
+                     const int32_t* in_perm, int32_t* out_coords, int* d_n_out, int out_cap,
+                     uint32_t* out_bitmap, uint32_t* out_prefix, int32_t* nbr,
+                     void* ws, size_t ws_bytes, dz_stream_t stream);
+
+/* ---- sparse convolution -------------------------------------------------------------------------------- */
+/* out[o,:] = act( (sum_k in[nbr[k][o],:] @ W[k]) * scale + shift (+ residual[o,:]) )
+ * Replaces SubMConv3d/SparseConv3d forward + BatchNorm1d(eval) + bias + residual add + ReLU
+ * (backbone3d.py:64-83,105-121).  weight packed (K, cin, cout) f32 (host side repacks spconv's
+ * (cout,KD,KH,KW,cin) layout).  mode: DZ_F32 exact-fp32 FMA, DZ_TF32 / DZ_BF16 tensor cores. */
+int dz_spconv_fwd(const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
+                  int out_cap, const float* weight, const float* scale, const float* shift,
+                  const float* residual, int relu, float* out, int cout, int mode, dz_stream_t stream);
+
+/* ---- BEV ------------------------------------------------------------------------------------------------ */
+/* SparseConvTensor.dense() + reshape(N, C*D, H, W) (height_compression.py:20-25) into NHWC:
+ * out[b,y,x,c*D+z] = feats[i,c].  out must be zero on entry. */
+int dz_sparse_to_bev(const float* feats, const int32_t* coords, const int* d_n, int cap, int c,
+                     int B, int D, int H, int W, float* out, dz_stream_t stream);
+/* NHWC conv2d (cross-correlation) with fused per-channel affine (folded BatchNorm2d / bias) and ReLU; output
+ * written at channel offset into a tensor with out_cstride channels (fused torch.cat, backbone2d.py:107-108).
+ * weight packed (KH, KW, cin, cout).  Replaces nn.Conv2d(+ZeroPad2d)+BatchNorm2d+ReLU stacks at
+ * backbone2d.py:34-48 and center_head.py:25-31,81-88. */
+int dz_conv2d_fwd(const float* in, int B, int H, int W, int cin, int in_cstride, const float* weight, int KH, int KW,
+                  int stride, int pad, const float* scale, const float* shift, int relu,
+                  float* out, int Ho, int Wo, int cout, int out_coff, int out_cstride, int mode,
+                  dz_stream_t stream);
+/* ConvTranspose2d with kernel == stride (backbone2d.py:52-60): out[b,y*s+dy,x*s+dx,co] = sum_ci in*W[dy,dx,ci,co]
+ * weight packed (s, s, cin, cout). */
+int dz_deconv2d_fwd(const float* in, int B, int H, int W, int cin, const float* weight, int s,
+                    const float* scale, const float* shift, int relu, float* out, int cout, int out_coff,
+                    int out_cstride, int mode, dz_stream_t stream);
+
+/* ---- CenterHead decode + NMS --------------------------------------------------------------------------- */
+/* centernet_utils.decode_bbox_from_heatmap / _topk (centernet_utils.py:138-230) on the fused head map
+ * (B,H,W,ch) NHWC with channel layout given by ch_* offsets.  Produces, per frame, up to K candidates in
+ * descending score order that pass POST_CENTER_LIMIT_RANGE and SCORE_THRESH:
+ *   cand_boxes (B,K,7), cand_scores (B,K), cand_labels (B,K) int32 (0-based class), d_cand_n (B). */
+size_t dz_centerhead_decode_ws_bytes(int B, int H, int W, int num_class, int K);
+int dz_centerhead_decode(const float* head, int B, int H, int W, int ch, int ch_center, int ch_z, int ch_dim,
+                         int ch_rot, int ch_iou, int ch_hm, int num_class, int K,
+                         const float* range_xyz6_host, const float* vsize_xyz3_host, int fmap_stride,
+                         const float* post_limit6_host, float score_thresh, int use_iou,
+                         float* cand_boxes, float* cand_scores, int32_t* cand_labels, int* d_cand_n,
+                         void* ws, size_t ws_bytes, dz_stream_t stream);
+/* Rotated-BEV NMS fully on device: replaces model_nms_utils.class_agnostic_nms -> nms_gpu
+ * (model_nms_utils.py:6-25, iou3d_nms_utils.py:154-170, iou3d_nms.cpp:114-160, iou3d_nms_kernel.cu:386-430).
+ * Input per frame: n<=cap boxes in descending score order.  Output: out (B, post_max, 9) rows
+ * [x,y,z,dx,dy,dz,heading,score,label+label_offset], zero padded, d_out_n (B). */
+size_t dz_nms_bev_ws_bytes(int B, int cap);
+int dz_nms_bev(const float* boxes, const float* scores, const int32_t* labels, const int* d_n, int B, int cap,
+               float thresh, int post_max, int label_offset, float* out, int* d_out_n,
+               void* ws, size_t ws_bytes, dz_stream_t stream);
+/* pairwise rotated BEV IoU (iou3d_nms_kernel.cu:370-384 boxes_iou_bev_kernel) */
+int dz_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* out, dz_stream_t stream);
+
+/* ---- refiner (GRM / PRM / CRM) ------------------------------------------------------------------------- */
+/* y = act((x @ W^T) * scale + shift): x (M,K) row-major, W (N,K) row-major (nn.Linear / 1x1 Conv layout).
+ * Replaces F.linear and the Conv1d/Conv2d(k=1)+BN+ReLU MLP stacks (utils/detzero_utils/model_utils.py:81-134). */
+int dz_linear_fwd(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift,
+                  int relu, float* y, int ldy, int mode, dz_stream_t stream);
+/* max over `group` consecutive rows: x (G*group, C) -> y (G, C)  (torch.max over points,
+ * position_transformer.py:109,118) */
+int dz_group_max(const float* x, int G, int group, int C, float* y, dz_stream_t stream);
+/* softmax(q k^T + key_padding) v per (batch, head); q already scaled.  q (B,Pq,H*dh), k/v (B,Pk,H*dh) with
+ * row strides ldq/ldk/ldv ; key_padding_mask (B,Pk) u8 (non-zero = masked, as masked_fill(-inf)) or NULL.
+ * Replaces multi_head_attention.py:266-286 without materialising the (B*H,Pq,Pk) score tensor. */
+int dz_attention_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                     const unsigned char* key_padding_mask, int B, int Pq, int Pk, int H, int dh, float* out,
+                     int ldo, int mode, dz_stream_t stream);
+/* y = LayerNorm(x + r) * gamma + beta over the last dim C (decoder.py:73-75,85-90) ; r may be NULL */
+int dz_layernorm_residual(const float* x, const float* r, const float* gamma, const float* beta, float eps,
+                          int M, int C, float* y, dz_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,324 @@
+"""GPU parity tests for the detector hot path: every kernel of libdetzero_b200 against the CPU oracle on the same
+seeded inputs (SURVEY.md §8c parity definitions).  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import det_ref, spconv_ref, weights
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs_from_nbr(nbr, n_out):
+    """neighbour table (K, cap) -> set of (k, in, out)"""
+    nbr = nbr[:, :n_out].cpu().numpy()
+    k, o = np.nonzero(nbr >= 0)
+    return set(zip(k.tolist(), nbr[k, o].tolist(), o.tolist()))
+
+
+def _pairs_from_oracle(pairs):
+    s = set()
+    for k, (i_in, i_out) in enumerate(pairs):
+        s.update(zip([k] * len(i_in), np.asarray(i_in).tolist(), np.asarray(i_out).tolist()))
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,max_voxels,rng_', [(20000, 200000, util.WAYMO_RANGE), (20000, 3000, util.WAYMO_RANGE),
+                                               (50000, 200000, util.SMALL_RANGE), (0, 100, util.WAYMO_RANGE),
+                                               (7, 100, util.WAYMO_RANGE)])
+def test_voxelize_hard_bit_exact(cuda, n, max_voxels, rng_):
+    """BASELINE config[0]: voxel coords / counts / order / features bit-exact vs the CPU voxelizer"""
+    from detzero_b200.spconv.utils import Point2VoxelGPU3d
+    pts = util.config1_cloud(n, seed=1, pc_range=rng_) if n else np.zeros((0, 5), np.float32)
+    if rng_ is util.SMALL_RANGE:
+        pts = np.concatenate([pts, util.clustered_cloud(n, 3)], axis=0)
+    ref = oracle.Point2VoxelCPU3d(util.VOXEL, rng_, 5, 5, max_voxels)
+    rv, rc, rn = ref.point_to_voxel(pts)
+    gen = Point2VoxelGPU3d(util.VOXEL, rng_, 5, 5, max_voxels, device=cuda)
+    v, c, m = gen.point_to_voxel(torch.from_numpy(pts).to(cuda))
+    assert v.shape[0] == rv.shape[0]
+    assert np.array_equal(c.cpu().numpy(), rc)
+    assert np.array_equal(m.cpu().numpy(), rn)
+    assert np.array_equal(v.cpu().numpy().view(np.uint32), rv.view(np.uint32))      # bit-exact features
+
+
+def test_voxelize_batch_and_mean(cuda):
+    from detzero_b200.spconv.utils import Point2VoxelGPU3d
+    clouds = [util.clustered_cloud(30000, 5), util.config1_cloud(10000, 6, util.SMALL_RANGE), util.clustered_cloud(500, 7)]
+    gen = Point2VoxelGPU3d(util.VOXEL, util.SMALL_RANGE, 5, 5, 20000, device=cuda)
+    pts_b = [torch.from_numpy(np.pad(p, ((0, 0), (1, 0)), constant_values=b)).to(cuda) for b, p in enumerate(clouds)]
+    r = gen.voxelize_batch(pts_b, xyz_off=1)
+    m = int(r['counters'][0].item())
+    ref = oracle.Point2VoxelCPU3d(util.VOXEL, util.SMALL_RANGE, 5, 5, 20000)
+    rv, rc, rn = [], [], []
+    for b, p in enumerate(clouds):
+        v, c, n = ref.point_to_voxel(p)
+        rv.append(v); rn.append(n); rc.append(np.pad(c, ((0, 0), (1, 0)), constant_values=b))
+    rv, rc, rn = np.concatenate(rv), np.concatenate(rc), np.concatenate(rn)
+    assert m == rv.shape[0]
+    assert np.array_equal(r['coords'][:m].cpu().numpy(), rc)
+    assert np.array_equal(r['num'][:m].cpu().numpy(), rn)
+    assert np.array_equal(r['voxels'][:m].cpu().numpy().view(np.uint32), rv.view(np.uint32))
+    mean_ref = det_ref.mean_vfe(rv, rn)
+    assert util.rel_err(r['mean'][:m].cpu(), mean_ref) < 1e-6
+    # the index handed to the backbone resolves every voxel to its own row
+    from detzero_b200 import ops
+    nbr = ops.rulebook_subm(r['coords'], r['counters'][0:1], r['cap'], r['index'], [1, 1, 1])
+    assert torch.equal(nbr[0, :m].cpu(), torch.arange(m, dtype=torch.int32))
+    # MeanVFE on pre-voxelized input (reference contract)
+    out = ops.mean_vfe(torch.from_numpy(rv).to(cuda), torch.from_numpy(rn).to(cuda))
+    assert util.rel_err(out.cpu(), mean_ref) < 1e-6
+
+
+def test_dynamic_mean_vfe(cuda):
+    from detzero_b200 import ops
+    clouds = [util.clustered_cloud(40000, 11, c=6), util.config1_cloud(15000, 12, util.SMALL_RANGE, c=6)]
+    pts = np.concatenate([np.pad(p, ((0, 0), (1, 0)), constant_values=b) for b, p in enumerate(clouds)]).astype(np.float32)
+    grid = [192, 192, 40]
+    mean_ref, coords_ref = det_ref.dynamic_mean_vfe(pts, util.SMALL_RANGE, util.VOXEL, grid)
+    feats, coords, d_m = ops.voxelize_dynamic_mean(torch.from_numpy(pts).to(cuda), 6, 2, util.SMALL_RANGE, util.VOXEL, grid, 60000)
+    m = int(d_m.item())
+    assert m == coords_ref.shape[0]
+    assert torch.equal(coords[:m].cpu(), coords_ref)                       # order = ascending (b,x,y,z) key
+    assert util.rel_err(feats[:m].cpu(), mean_ref) < 1e-5                  # atomics: sum order differs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _sparse_input(cuda, seed, B, shape, density, cin):
+    idx = weights.random_sparse_coords(seed, B, shape, density)
+    f = torch.from_numpy(np.random.default_rng(seed + 1).normal(0, 1, (len(idx), cin)).astype(np.float32))
+    return idx, f
+
+
+@pytest.mark.parametrize('ks,stride,pad', [(3, 1, 1), (3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0)])
+def test_rulebook_set_exact(cuda, ks, stride, pad):
+    from detzero_b200 import ops
+    from detzero_b200.spconv.pytorch import SparseConvTensor, _triple
+    shape, B = [11, 40, 36], 2
+    idx, f = _sparse_input(cuda, 21, B, shape, 0.08, 16)
+    t = SparseConvTensor(f.to(cuda), torch.from_numpy(idx).to(cuda), shape, B)
+    n = len(idx)
+    if stride == 1:
+        nbr = ops.rulebook_subm(t._idx, t._count, t._cap, t.grid_index(), _triple(ks))
+        got = _pairs_from_nbr(nbr, n)
+        want = _pairs_from_oracle(spconv_ref.rulebook_subm(idx, shape, ks))
+        assert got == want
+    else:
+        oc, d_n, oi, nbr, odhw = ops.rulebook_conv(t._idx, t._count, t._cap, t.grid_index(), _triple(ks), _triple(stride),
+                                                   _triple(pad), out_cap=n * 2)
+        ref_idx, ref_shape, ref_pairs = spconv_ref.rulebook_conv(idx, shape, ks, stride, pad)
+        m = int(d_n.item())
+        assert odhw == ref_shape and m == ref_idx.shape[0]
+        assert np.array_equal(oc[:m].cpu().numpy(), ref_idx)                # sorted (b,z,y,x): bit-exact site list
+        assert _pairs_from_nbr(nbr, m) == _pairs_from_oracle(ref_pairs)
+
+
+@pytest.mark.parametrize('cin,cout', [(5, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
+def test_spconv_fwd_fp32(cuda, cin, cout):
+    """fp32-exact mode: <= 1e-5 rel (summation order only), with the fused affine/residual/ReLU epilogue"""
+    from detzero_b200 import ops
+    from detzero_b200.spconv.pytorch import SparseConvTensor
+    shape, B = [9, 30, 30], 2
+    idx, f = _sparse_input(cuda, 31 + cin, B, shape, 0.12, cin)
+    n = len(idx)
+    g = np.random.default_rng(5)
+    w = torch.from_numpy(g.normal(0, 0.2, (cout, 3, 3, 3, cin)).astype(np.float32))
+    scale = torch.from_numpy(g.uniform(0.5, 1.5, cout).astype(np.float32))
+    shift = torch.from_numpy(g.normal(0, 0.1, cout).astype(np.float32))
+    res = torch.from_numpy(g.normal(0, 1, (n, cout)).astype(np.float32))
+    ref = spconv_ref.sparse_conv_native(f, w, spconv_ref.rulebook_subm(idx, shape, 3), n)
+    ref = torch.relu(ref * scale + shift + res)
+    t = SparseConvTensor(f.to(cuda), torch.from_numpy(idx).to(cuda), shape, B)
+    nbr = ops.rulebook_subm(t._idx, t._count, t._cap, t.grid_index(), [3, 3, 3])
+    wp = w.reshape(cout, 27, cin).permute(1, 2, 0).contiguous().to(cuda)
+    out = ops.spconv_fwd(t._feat, nbr, t._count, n, wp, scale.to(cuda), shift.to(cuda), res.to(cuda), True)
+    assert util.rel_err(out.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize('kind', ['VoxelBackBone8x', 'VoxelResBackBone8x'])
+def test_backbone3d_vs_oracle(cuda, kind):
+    from detzero_b200.det import cp_modules
+    cfg = util.model_cfg(kind).BACKBONE_3D
+    m = cp_modules[kind](model_cfg=cfg, input_channels=5, grid_size=[192, 192, 40]).eval()
+    sd = weights.load_seeded(m, 7)
+    m = m.to(cuda)
+    clouds = [util.clustered_cloud(25000, 41), util.clustered_cloud(12000, 42)]
+    ref = oracle.Point2VoxelCPU3d(util.VOXEL, util.SMALL_RANGE, 5, 5, 40000)
+    feats, coords = [], []
+    for b, p in enumerate(clouds):
+        v, c, n = ref.point_to_voxel(p)
+        feats.append(det_ref.mean_vfe(v, n)); coords.append(np.pad(c, ((0, 0), (1, 0)), constant_values=b))
+    feats, coords = torch.cat(feats), np.concatenate(coords).astype(np.int32)
+    want = det_ref.voxel_backbone(sd, '', feats, coords, m.sparse_shape, 2, res=(kind == 'VoxelResBackBone8x'))
+    bd = {'voxel_features': feats.to(cuda), 'voxel_coords': torch.from_numpy(coords).to(cuda), 'batch_size': 2}
+    with torch.no_grad():
+        bd = m(bd)
+    for name, got in list(bd['multi_scale_3d_features'].items()) + [('out', bd['encoded_spconv_tensor'])]:
+        w = want[name]
+        assert np.array_equal(got.indices.cpu().numpy(), w.idx), name       # same sites, same (sorted) order
+        assert got.spatial_shape == w.shape
+        assert util.rel_err(got.features.cpu(), w.f) < 2e-5, name
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('cin,cout,k,stride,pad,H,W', [(64, 64, 3, 1, 1, 24, 20), (256, 128, 3, 1, 1, 13, 11),
+                                                       (128, 256, 3, 2, 1, 24, 24), (64, 12, 3, 1, 1, 9, 10),
+                                                       (128, 256, 1, 1, 0, 12, 12), (384, 12, 3, 1, 1, 8, 8)])
+def test_conv2d_fp32(cuda, cin, cout, k, stride, pad, H, W):
+    from detzero_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * 0.05
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x, w, None, stride, pad) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    out = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), w.permute(2, 3, 1, 0).contiguous().to(cuda), stride, pad,
+                     scale.to(cuda), shift.to(cuda), True)
+    assert util.rel_err(out.permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize('s', [1, 2])
+def test_deconv2d_fp32_concat(cuda, s):
+    from detzero_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 64, 7, 9, generator=g)
+    w = torch.randn(64, 32, s, s, generator=g) * 0.1
+    ref = torch.nn.functional.conv_transpose2d(x, w, None, stride=s)
+    out = torch.zeros(2, 7 * s, 9 * s, 48, device=cuda)
+    ops.deconv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), w.permute(2, 3, 0, 1).contiguous().to(cuda), None, None, False,
+                 out=out, out_coff=16)
+    assert util.rel_err(out[..., 16:].permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+    assert out[..., :16].abs().max().item() == 0
+
+
+def test_sparse_to_bev(cuda):
+    from detzero_b200.spconv.pytorch import SparseConvTensor
+    shape, B = [2, 24, 24], 2
+    idx, f = _sparse_input(cuda, 51, B, shape, 0.2, 128)
+    t = SparseConvTensor(f.to(cuda), torch.from_numpy(idx).to(cuda), shape, B)
+    ref = spconv_ref.dense_from_sparse(f, idx, shape, B)
+    assert torch.equal(t.dense().cpu(), ref)
+
+
+def _dense_models(cuda, seed=9):
+    from detzero_b200.det import cp_modules
+    cfg = util.model_cfg()
+    b2d = cp_modules['BaseBEVBackbone'](model_cfg=cfg.BACKBONE_2D, input_channels=256).eval()
+    head = cp_modules['CenterHead'](model_cfg=cfg.DENSE_HEAD, input_channels=512, num_class=3, class_names=util.CLASS_NAMES,
+                                    grid_size=[192, 192, 40], point_cloud_range=util.SMALL_RANGE, voxel_size=util.VOXEL).eval()
+    sd2, sdh = weights.load_seeded(b2d, seed), weights.load_seeded(head, seed + 1)
+    return cfg, b2d.to(cuda), head.to(cuda), sd2, sdh
+
+
+def test_bev_backbone_and_head_maps(cuda):
+    cfg, b2d, head, sd2, sdh = _dense_models(cuda)
+    x = torch.randn(2, 256, 24, 24, generator=torch.Generator().manual_seed(1))
+    ref2d = det_ref.bev_backbone(sd2, '', x, [5, 5], [1, 2], [1, 2])
+    names = ['center', 'center_z', 'dim', 'rot', 'iou', 'hm']
+    refmaps = det_ref.center_head_maps(sdh, '', ref2d, names)
+    with torch.no_grad():
+        bd = b2d({'spatial_features': x.to(cuda)})
+        assert bd['spatial_features_2d'].shape == ref2d.shape
+        assert util.rel_err(bd['spatial_features_2d'].cpu(), ref2d) < 2e-5
+        bd['batch_size'] = 2
+        bd = head(bd)
+    for n in names:
+        assert util.rel_err(head.forward_ret_dict['pred_dicts'][0][n].cpu(), refmaps[n]) < 5e-5, n
+
+
+def test_iou_and_nms(cuda):
+    from detzero_b200 import ops
+    g = np.random.default_rng(2)
+    n = 300
+    boxes = np.concatenate([g.uniform(-20, 20, (n, 2)), g.uniform(-1, 1, (n, 1)), g.uniform(1.5, 5, (n, 2)),
+                            g.uniform(1, 2, (n, 1)), g.uniform(-3.2, 3.2, (n, 1))], axis=1).astype(np.float32)
+    boxes[100:200, :2] = boxes[:100, :2] + g.normal(0, 0.3, (100, 2)).astype(np.float32)     # overlapping clusters
+    boxes[100:200, 3:7] = boxes[:100, 3:7] + g.normal(0, 0.05, (100, 4)).astype(np.float32)
+    iou_ref = oracle.boxes_iou_bev(boxes, boxes)
+    iou = ops.boxes_iou_bev(torch.from_numpy(boxes).to(cuda), torch.from_numpy(boxes).to(cuda)).cpu().numpy()
+    assert np.abs(iou - iou_ref).max() < 1e-4
+    scores = np.sort(g.uniform(0.05, 1, n).astype(np.float32))[::-1].copy()
+    keep_ref = oracle.nms_bev_sorted(boxes, 0.7)
+    margin = np.abs(iou_ref - 0.7)
+    assert margin[np.triu_indices(n, 1)].min() > 1e-4, 'test boxes too close to the threshold'
+    cap = 512
+    pb = np.zeros((1, cap, 7), np.float32); pb[0, :n] = boxes
+    ps = np.zeros((1, cap), np.float32); ps[0, :n] = scores
+    out, d_out = ops.nms_bev(torch.from_numpy(pb).to(cuda), torch.from_numpy(ps).to(cuda),
+                             torch.zeros((1, cap), dtype=torch.int32, device=cuda),
+                             torch.tensor([n], dtype=torch.int32, device=cuda), 0.7, 500, label_offset=1)
+    k = int(d_out.item())
+    assert k == len(keep_ref)
+    assert np.array_equal(out[0, :k, :7].cpu().numpy(), boxes[keep_ref])
+    assert np.array_equal(out[0, :k, 7].cpu().numpy(), scores[keep_ref])
+    assert out[0, k:].abs().max().item() == 0
+
+
+def test_decode_and_nms_vs_oracle(cuda):
+    from detzero_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    B, H, W = 2, 24, 24
+    maps = {'center': torch.rand(B, 2, H, W, generator=g), 'center_z': torch.randn(B, 1, H, W, generator=g),
+            'dim': torch.randn(B, 3, H, W, generator=g) * 0.3 + 0.8, 'rot': torch.randn(B, 2, H, W, generator=g),
+            'iou': torch.rand(B, 1, H, W, generator=g) * 1.4 - 0.2, 'hm': torch.randn(B, 3, H, W, generator=g) * 2 - 1}
+    post = dict(MAX_OBJ_PER_SAMPLE=500, SCORE_THRESH=0.03, POST_CENTER_LIMIT_RANGE=[-80, -80, -10.0, 80, 80, 10.0],
+                NMS_THRESH=0.7, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500)
+    want = det_ref.generate_predicted_boxes(maps, util.SMALL_RANGE, util.VOXEL, 8, post, use_iou=True)
+    order = ['center', 'center_z', 'dim', 'rot', 'iou', 'hm']
+    hm = torch.cat([maps[k] for k in order], dim=1).permute(0, 2, 3, 1).contiguous().to(cuda)
+    layout, off = {}, 0
+    for k in order:
+        layout[k] = off; off += maps[k].shape[1]
+    boxes, scores, labels, d_n = ops.centerhead_decode(hm, layout, 3, 500, util.SMALL_RANGE, util.VOXEL, 8,
+                                                       post['POST_CENTER_LIMIT_RANGE'], 0.03, True)
+    out, d_out = ops.nms_bev(boxes, scores, labels, d_n, 0.7, 500, label_offset=1)
+    for b in range(B):
+        k = int(d_out[b].item())
+        assert k == want[b]['pred_boxes'].shape[0]
+        assert (out[b, :k, :7].cpu() - want[b]['pred_boxes']).abs().max().item() < 1e-3       # metres / radians
+        assert (out[b, :k, 7].cpu() - want[b]['pred_scores']).abs().max().item() < 1e-6
+        assert torch.equal(out[b, :k, 8].cpu().long(), want[b]['pred_labels'])
+
+
+def test_centerpoint_end_to_end(cuda):
+    """raw points -> final boxes through the registry-built CenterPoint vs the CPU oracle chain"""
+    from detzero_b200.det import build_network, load_data_to_gpu
+    from detzero_b200.det.dataset import SyntheticWaymoDataset, default_waymo_1sweep_cfg
+    dcfg = default_waymo_1sweep_cfg()
+    dcfg.POINT_CLOUD_RANGE = util.SMALL_RANGE
+    ds = SyntheticWaymoDataset(dcfg, util.CLASS_NAMES, training=False, num_frames=2, n_points=30000)
+    cfg = util.model_cfg('VoxelResBackBone8x')
+    model = build_network(cfg, 3, ds).eval()
+    sd = weights.load_seeded(model, 21)
+    model = model.to(cuda)
+    clouds = [util.clustered_cloud(30000, 61, c=6), util.clustered_cloud(20000, 62, c=6)]
+    items = []
+    for i, p in enumerate(clouds):
+        d = {'points': p, 'frame_id': str(i)}
+        items.append(ds.data_processor.forward(ds.point_feature_encoder.forward(d)))
+    batch = ds.collate_batch(items)
+    load_data_to_gpu(batch, cuda)
+    with torch.no_grad():
+        pred_dicts, _ = model(batch)
+    # oracle chain
+    vox = oracle.Point2VoxelCPU3d(util.VOXEL, util.SMALL_RANGE, 5, 5, 200000)
+    feats, coords = [], []
+    for b, d in enumerate(items):
+        v, c, n = vox.point_to_voxel(d['points'])
+        feats.append(det_ref.mean_vfe(v, n)); coords.append(np.pad(c, ((0, 0), (1, 0)), constant_values=b))
+    lv = det_ref.voxel_backbone(sd, 'backbone3d.', torch.cat(feats), np.concatenate(coords), [41, 192, 192], 2, res=True)
+    sf = det_ref.height_compression(lv['out'])
+    s2d = det_ref.bev_backbone(sd, 'backbone2d.', sf, [5, 5], [1, 2], [1, 2])
+    maps = det_ref.center_head_maps(sd, 'dense_head.', s2d, ['center', 'center_z', 'dim', 'rot', 'iou', 'hm'])
+    post = dict(MAX_OBJ_PER_SAMPLE=500, SCORE_THRESH=0.03, POST_CENTER_LIMIT_RANGE=[-80, -80, -10.0, 80, 80, 10.0],
+                NMS_THRESH=0.7, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500)
+    want = det_ref.generate_predicted_boxes(maps, util.SMALL_RANGE, util.VOXEL, 8, post, use_iou=True)
+    assert util.rel_err(batch['spatial_features_2d'].cpu(), s2d) < 1e-4
+    for b in range(2):
+        got = pred_dicts[b]
+        assert got['pred_boxes'].shape[0] == want[b]['pred_boxes'].shape[0]
+        assert (got['pred_boxes'].cpu() - want[b]['pred_boxes']).abs().max().item() < 1e-3
+        assert (got['pred_scores'].cpu() - want[b]['pred_scores']).abs().max().item() < 1e-5
+        assert torch.equal(got['pred_labels'].cpu(), want[b]['pred_labels'])
