@@ -95,7 +95,8 @@ def cfg_from_list(cfg_list, config):
                 ck, cv = src.split(':')
                 d[sub][ck] = type(d[sub][ck])(cv)
         elif type(value) != type(d[sub]) and isinstance(d[sub], list):
-            d[sub] = [type(d[sub][0])(x) for x in value.split(',')]
+            items = list(value) if isinstance(value, (tuple, list)) else value.split(',')
+            d[sub] = [type(d[sub][0])(x) for x in items]
         else:
             assert type(value) == type(d[sub]), 'type %s does not match %s' % (type(value), type(d[sub]))
             d[sub] = value

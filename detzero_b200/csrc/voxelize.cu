@@ -390,7 +390,7 @@ extern "C" int dz_voxelize_hard(const float* points, int n, int point_stride, in
                                 int* d_counters, int B, int iD, int iH, int iW, uint32_t* index_bitmap,
                                 uint32_t* index_prefix, int32_t* index_perm, void* ws, size_t ws_bytes,
                                 dz_stream_t stream) {
-    DZ_CHECK_ARG(points && voxels && coords && num_per_voxel && d_counters && index_bitmap && index_prefix && index_perm);
+    DZ_CHECK_ARG((points || n == 0) && voxels && coords && num_per_voxel && d_counters && index_bitmap && index_prefix && index_perm);
     DZ_CHECK_ARG(n >= 0 && c >= 1 && xyz_off >= 0 && xyz_off + c <= point_stride && point_stride <= VOX_MAX_STRIDE && c >= 3);
     DZ_CHECK_ARG(max_pts >= 1 && max_voxels >= 1 && batch_idx >= 0 && batch_idx < B);
     DZ_CHECK_ARG(grid_zyx3[0] <= iD && grid_zyx3[1] <= iH && grid_zyx3[2] <= iW);
@@ -534,7 +534,7 @@ extern "C" size_t dz_voxelize_dynamic_ws_bytes(int n_points, int cap, int B, int
 extern "C" int dz_voxelize_dynamic_mean(const float* points, int n, int c, int B, const float* range6, const float* vsize3,
                                         const int* grid_xyz3, float* feats, int32_t* coords, int cap, int* d_m,
                                         void* ws, size_t ws_bytes, dz_stream_t stream) {
-    DZ_CHECK_ARG(points && feats && coords && d_m && n >= 0 && c >= 3 && 1 + c <= VOX_MAX_STRIDE && B >= 1 && cap >= 1);
+    DZ_CHECK_ARG((points || n == 0) && feats && coords && d_m && n >= 0 && c >= 3 && 1 + c <= VOX_MAX_STRIDE && B >= 1 && cap >= 1);
     if (ws_bytes < dz_voxelize_dynamic_ws_bytes(n, cap, B, grid_xyz3[0], grid_xyz3[1], grid_xyz3[2])) {
         dz_set_error("dz_voxelize_dynamic_mean: workspace too small"); return DZ_ERR_WORKSPACE;
     }
