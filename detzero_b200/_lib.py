@@ -47,6 +47,7 @@ _SIGS = {
     'dz_group_max': (ci, [vp, ci, ci, ci, vp, vp]),
     'dz_attention_fwd': (ci, [vp, ci, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp]),
     'dz_layernorm_residual': (ci, [vp, vp, vp, vp, cf, ci, ci, vp, vp]),
+    'dz_add': (ci, [vp, vp, sz, vp, vp]),
 }
 
 

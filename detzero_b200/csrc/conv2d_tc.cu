@@ -1,0 +1,190 @@
+// conv2d_tc.cu -- NHWC conv2d as a tcgen05 implicit GEMM (TF32 inputs, fp32 accumulation in TMEM), sm_100a.
+//
+// Replaces the cuDNN convolutions of BaseBEVBackbone / CenterHead (backbone2d.py:34-81, center_head.py:25-31,81-88);
+// the reference runs them with TF32 tensor cores too (torch.backends.cudnn.allow_tf32 defaults to True).
+//
+// Design: output tile = 8 x 16 pixel patch (M = 128) x BN output channels.  For every filter tap (r,s) and every
+// 32-channel slice of Cin, ONE 4-D TMA box load of the shifted input patch lands in shared memory already in the
+// canonical K-major 128B-swizzled UMMA layout (row = pixel, 128 B = 32 fp32 channels); out-of-image pixels are
+// zero-filled by the TMA unit, which implements the conv padding (and ZeroPad2d) for free.  Weights are a 2-D TMA
+// load of W[cout][(r,s,cin)].  One elected thread issues tcgen05.mma (M=128, N=BN, K=8) into a TMEM accumulator;
+// a ring of mbarrier-guarded stages overlaps TMA with MMA; 4 epilogue warps read TMEM (tcgen05.ld), apply the
+// folded BatchNorm / bias / ReLU and write NHWC rows (optionally into a channel slice / strided pixels: fused
+// torch.cat and ConvTranspose2d with kernel == stride).
+#include "common.cuh"
+#include "conv2d.cuh"
+#include "tc.cuh"
+
+namespace tc {
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+}  // namespace tc
+
+static constexpr int CT_TH = 8, CT_TW = 16, CT_BK = 32;       // pixel patch, channels per k-step group (128 B)
+static constexpr int CT_A_BYTES = CT_TH * CT_TW * CT_BK * 4;  // 16 KB
+static constexpr int CT_THREADS = 192;                        // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
+
+template <int BN>
+struct CtCfg {
+    static constexpr int B_BYTES = BN * CT_BK * 4;
+    static constexpr int STAGE_BYTES = CT_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Conv2dParams p, int tiles_x,
+              int tiles_y) {
+    using Cfg = CtCfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tmem_full = empty + Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int mt = blockIdx.x;
+    const int tx0 = (mt % tiles_x) * CT_TW; mt /= tiles_x;
+    const int ty0 = (mt % tiles_y) * CT_TH;
+    const int b = mt / tiles_y;
+    const int n0 = blockIdx.y * BN;
+    const int cchunks = p.cin / CT_BK;
+    const int iters = p.KH * p.KW * cchunks;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % Cfg::STAGES;
+                tc::mbar_wait(empty + s, ((it / Cfg::STAGES) & 1) ^ 1);
+                unsigned char* sa = smem + s * Cfg::STAGE_BYTES;
+                unsigned char* sb = sa + CT_A_BYTES;
+                const int tap = it / cchunks, cc = it - tap * cchunks;
+                const int r = tap / p.KW, sx = tap - r * p.KW;
+                tc::mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
+                tc::tma_load_4d(sa, &tmA, full + s, cc * CT_BK, tx0 * p.stride + sx - p.pad, ty0 * p.stride + r - p.pad, b);
+                tc::tma_load_2d(sb, &tmB, full + s, tap * p.cin + cc * CT_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::instr_desc(2, 128, BN < 16 ? 16 : BN);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % Cfg::STAGES;
+                tc::mbar_wait(full + s, (it / Cfg::STAGES) & 1);
+                tc::tcgen05_fence_after();
+                const uint32_t sa = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint64_t adesc = tc::smem_desc_sw128(sa), bdesc = tc::smem_desc_sw128(sa + CT_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < CT_BK / 8; ++k)            // K = 8 tf32 = 32 bytes per instruction
+                    tc::mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+                tc::mma_commit(empty + s);                      // frees the stage once these MMAs have read it
+            }
+            tc::mma_commit(tmem_full);
+        }
+    } else {
+        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                          // pixel index inside the 8x16 patch
+        const int y = ty0 + row / CT_TW, x = tx0 + row % CT_TW;
+        const bool valid = (y < p.Ho) && (x < p.Wo);
+        float* orow = p.out + (((size_t)b * p.OH + (y * p.os + p.oy0)) * p.OW + (x * p.os + p.ox0)) * p.out_cstride + p.out_coff;
+        tc::mbar_wait(tmem_full, 0);
+        tc::tcgen05_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + c0 + j;
+                    if (n >= p.cout) break;
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (p.scale) { float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n)); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+                    if (p.shift) { float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n)); o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w; }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(orow + n) = o;
+                }
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+template <int BN>
+static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+    using Cfg = CtCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        configured = true;
+    }
+    int tiles_x = dz_cdiv(p.Wo, CT_TW), tiles_y = dz_cdiv(p.Ho, CT_TH);
+    dim3 grid(tiles_x * tiles_y * p.B, dz_cdiv(p.cout, BN));
+    k_conv2d_tf32<BN><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, p, tiles_x, tiles_y);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
+}
+
+// p.w must be in (cout, KH, KW, cin) layout for this path
+int dz_conv2d_fwd_tc(const Conv2dParams& p, int mode, cudaStream_t st) {
+    if (mode != DZ_TF32) { dz_set_error("dz_conv2d_fwd: tensor-core mode %d not built (tf32 only)", mode); return DZ_ERR_UNSUPPORTED; }
+    if (p.cin % CT_BK != 0 || p.in_cstride % 4 != 0 || p.cout % 4 != 0 || p.out_cstride % 4 != 0 || p.out_coff % 4 != 0) {
+        dz_set_error("dz_conv2d_fwd(tf32): needs cin %% 32 == 0 and 16-byte aligned channel slices (cin=%d cout=%d)", p.cin, p.cout);
+        return DZ_ERR_UNSUPPORTED;
+    }
+    tc::EncodeTiledFn enc = tc::get_encode_tiled();
+    if (!enc) { dz_set_error("cuTensorMapEncodeTiled unavailable"); return DZ_ERR_CUDA; }
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)p.in_cstride, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.in_cstride * 4, (cuuint64_t)p.W * p.in_cstride * 4, (cuuint64_t)p.H * p.W * p.in_cstride * 4};
+        // with a traversal stride s the box spans (n-1)*s+1 input elements and delivers n of them
+        cuuint32_t box[4] = {(cuuint32_t)CT_BK, (cuuint32_t)((CT_TW - 1) * p.stride + 1), (cuuint32_t)((CT_TH - 1) * p.stride + 1), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
+    int bn = p.cout > 128 ? 128 : (p.cout > 64 ? 128 : (p.cout > 32 ? 64 : 32));
+    {
+        cuuint64_t ktot = (cuuint64_t)p.KH * p.KW * p.cin;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)p.cout};
+        cuuint64_t strides[1] = {ktot * 4};
+        cuuint32_t box[2] = {(cuuint32_t)CT_BK, (cuuint32_t)bn};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
+    switch (bn) {
+        case 128: return launch_tf32<128>(p, tmA, tmB, st);
+        case 64: return launch_tf32<64>(p, tmA, tmB, st);
+        default: return launch_tf32<32>(p, tmA, tmB, st);
+    }
+}

@@ -254,3 +254,22 @@ extern "C" int dz_layernorm_residual(const float* x, const float* r, const float
     DZ_LAUNCH_CHECK();
     return DZ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// out = a + b (with_pos_embed, decoder.py:45-46)
+__global__ void k_add(const float4* __restrict__ a, const float4* __restrict__ b, size_t n4, float4* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 x = __ldg(a + i), y = __ldg(b + i);
+        out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    }
+}
+
+extern "C" int dz_add(const float* a, const float* b, size_t n, float* out, dz_stream_t stream) {
+    DZ_CHECK_ARG(a && b && out && n % 4 == 0);
+    if (n == 0) return DZ_OK;
+    int blocks = (int)((n / 4 + 255) / 256);
+    if (blocks > DZ_NUM_SMS * 16) blocks = DZ_NUM_SMS * 16;
+    k_add<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, n / 4, (float4*)out);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
+}

@@ -1,14 +1,10 @@
 // tc_stubs.cu -- tensor-core (tcgen05) entry points that are not implemented yet fail loudly: there is no silent
 // fallback to the fp32 path.
 #include "common.cuh"
-#include "conv2d.cuh"
 
 int dz_spconv_fwd_tc(const float*, int, const int32_t*, int, int, const int*, int, const float*, const float*, const float*,
                      const float*, int, float*, int, int mode, cudaStream_t) {
     dz_set_error("dz_spconv_fwd: tensor-core mode %d not built", mode); return DZ_ERR_UNSUPPORTED;
-}
-int dz_conv2d_fwd_tc(const Conv2dParams&, int mode, cudaStream_t) {
-    dz_set_error("dz_conv2d_fwd: tensor-core mode %d not built", mode); return DZ_ERR_UNSUPPORTED;
 }
 int dz_linear_fwd_tc(const float*, int, int, const float*, int, const float*, const float*, int, float*, int, int mode, cudaStream_t) {
     dz_set_error("dz_linear_fwd: tensor-core mode %d not built", mode); return DZ_ERR_UNSUPPORTED;

@@ -32,23 +32,22 @@ _pack_cache = {}
 
 def _cached(key_obj, tensors, fn):
     ver = tuple((t._version, t.data_ptr()) for t in tensors if t is not None)
-    hit = _pack_cache.get(id(key_obj))
+    key = (id(key_obj[0]), key_obj[1]) if isinstance(key_obj, tuple) else id(key_obj)
+    hit = _pack_cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
     with torch.no_grad():
         val = fn()
-    _pack_cache[id(key_obj)] = (ver, val)
+    _pack_cache[key] = (ver, val)
     return val
 
 
-def pack_conv_weight(conv):
-    """nn.Conv2d weight (Cout,Cin,KH,KW) -> (KH,KW,Cin,Cout)"""
-    return _cached(conv, [conv.weight], lambda: conv.weight.detach().permute(2, 3, 1, 0).contiguous().float())
+def pack_conv_weight(conv, mode):
+    return _cached((conv, mode), [conv.weight], lambda: ops.pack_conv_weight(conv.weight, mode))
 
 
-def pack_deconv_weight(deconv):
-    """nn.ConvTranspose2d weight (Cin,Cout,s,s) -> (s,s,Cin,Cout)"""
-    return _cached(deconv, [deconv.weight], lambda: deconv.weight.detach().permute(2, 3, 0, 1).contiguous().float())
+def pack_deconv_weight(deconv, mode):
+    return _cached((deconv, mode), [deconv.weight], lambda: ops.pack_deconv_weight(deconv.weight, mode))
 
 
 def run_conv_stack(seq, x, mode, out=None, out_coff=0):
@@ -79,10 +78,11 @@ def run_conv_stack(seq, x, mode, out=None, out_coff=0):
         o, off = (out, out_coff) if last else (None, 0)
         if isinstance(m, nn.ConvTranspose2d):
             assert m.kernel_size[0] == m.stride[0] and m.padding[0] == 0
-            x = ops.deconv2d(x, pack_deconv_weight(m), scale, shift, relu, out=o, out_coff=off, mode=mode)
+            x = ops.deconv2d(x, pack_deconv_weight(m, mode), (m.kernel_size[0], m.in_channels, m.out_channels), scale, shift,
+                             relu, out=o, out_coff=off, mode=mode)
         else:
-            x = ops.conv2d(x, pack_conv_weight(m), int(m.stride[0]), int(m.padding[0]) + pad_extra, scale, shift, relu,
-                           out=o, out_coff=off, mode=mode)
+            x = ops.conv2d(x, pack_conv_weight(m, mode), (m.kernel_size[0], m.kernel_size[1], m.in_channels, m.out_channels),
+                           int(m.stride[0]), int(m.padding[0]) + pad_extra, scale, shift, relu, out=o, out_coff=off, mode=mode)
     return x
 
 
@@ -251,27 +251,30 @@ class CenterHead(nn.Module):
             params += [fc[0][0].weight, fc[0][0].bias, fc[0][1].weight, fc[0][1].bias, fc[0][1].running_mean,
                        fc[0][1].running_var, fc[1].weight, fc[1].bias]
 
+        mode = self.mode
+
         def build():
             sc = getattr(head, names[0])[0][0].in_channels
             w1, s1, b1 = [], [], []
             outs = [getattr(head, n)[1].out_channels for n in names]
             tot = sum(outs)
             tot_pad = (tot + 3) // 4 * 4
-            w2 = torch.zeros((3, 3, sc * len(names), tot_pad), dtype=torch.float32, device=params[0].device)
+            w2 = torch.zeros((tot_pad, sc * len(names), 3, 3), dtype=torch.float32, device=params[0].device)   # OIHW
             b2 = torch.zeros((tot_pad,), dtype=torch.float32, device=params[0].device)
             off, layout = 0, {}
             for bi, n in enumerate(names):
                 fc = getattr(head, n)
-                w1.append(fc[0][0].weight.detach().permute(2, 3, 1, 0).float())           # (3,3,sc,sc)
+                w1.append(fc[0][0].weight.detach().float())                                 # (sc, sc, 3, 3)
                 sc_, sh_ = fold_bn(fc[0][1], fc[0][0].bias)
                 s1.append(sc_); b1.append(sh_)
-                w2[:, :, bi * sc:(bi + 1) * sc, off:off + outs[bi]] = fc[1].weight.detach().permute(2, 3, 1, 0).float()
+                w2[off:off + outs[bi], bi * sc:(bi + 1) * sc] = fc[1].weight.detach().float()   # block diagonal
                 b2[off:off + outs[bi]] = fc[1].bias.detach().float()
                 layout[n] = off
                 off += outs[bi]
-            return (torch.cat(w1, dim=3).contiguous(), torch.cat(s1).contiguous(), torch.cat(b1).contiguous(),
-                    w2.contiguous(), b2, layout, tot, tot_pad)
-        return _cached(head, params, build)
+            w1 = torch.cat(w1, dim=0)                                                      # (sc*nb, sc, 3, 3)
+            return (ops.pack_conv_weight(w1, mode), (3, 3, sc, sc * len(names)), torch.cat(s1).contiguous(),
+                    torch.cat(b1).contiguous(), ops.pack_conv_weight(w2, mode), (3, 3, sc * len(names), tot_pad), b2, layout)
+        return _cached((head, self.mode), params, build)
 
     def forward(self, data_dict):
         if self.training:
@@ -282,9 +285,9 @@ class CenterHead(nn.Module):
         pred_dicts, padded, counts = [], [], []
         post = self.model_cfg.POST_PROCESSING
         for idx, head in enumerate(self.heads_list):
-            w1, s1, b1, w2, b2, layout, tot, tot_pad = self._fused_head(head)
-            h1 = ops.conv2d(x, w1, 1, 1, s1, b1, True, mode=self.mode)
-            hm = ops.conv2d(h1, w2, 1, 1, None, b2, False, mode=self.mode)               # (B,H,W,tot_pad)
+            w1, k1, s1, b1, w2, k2, b2, layout = self._fused_head(head)
+            h1 = ops.conv2d(x, w1, k1, 1, 1, s1, b1, True, mode=self.mode)
+            hm = ops.conv2d(h1, w2, k2, 1, 1, None, b2, False, mode=self.mode)           # (B,H,W,tot_pad)
             nchw = _nchw_view(hm)
             outs = {n: nchw[:, layout[n]:layout[n] + getattr(head, n)[1].out_channels] for n in self.head_order}
             pred_dicts.append(outs)

@@ -17,6 +17,32 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_launches = 0
+_trace = None
+
+
+def _count(n):
+    """bookkeeping of how many of OUR kernels were enqueued (bench.py reports it as gpu_launches)"""
+    global _launches
+    _launches += n
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def enable_spconv_trace(on):
+    """bench.py roofline: record a CUDA-event pair + shapes for every sparse-conv launch"""
+    global _trace
+    _trace = [] if on else None
+    return _trace
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -66,6 +92,7 @@ def grid_index_from_coords(coords, d_n, cap, B, dhw, with_perm=True):
     ws = workspace(scan_ws_bytes(gi.words), coords.device)
     check(lib().dz_grid_index_from_coords(_p(coords), _p(d_n), cap, gi.B, *gi.dhw, _p(gi.bitmap), _p(gi.prefix),
                                           _p(gi.perm), _p(total), _p(ws), ws.numel(), _stream()), 'grid_index_from_coords')
+    _count(5)
     return gi
 
 
@@ -82,6 +109,7 @@ def voxelize_hard(points, xyz_off, c, pc_range, voxel_size, grid_zyx, max_pts, m
                                  max_pts, max_voxels, batch_idx, _p(voxels), _p(coords), _p(num), _p(mean), cap,
                                  _p(counters), index.B, *index.dhw, _p(index.bitmap), _p(index.prefix), _p(index.perm),
                                  _p(ws), ws.numel(), _stream()), 'voxelize_hard')
+    _count(11)
 
 
 def mean_vfe(voxels, num_i32):
@@ -89,6 +117,7 @@ def mean_vfe(voxels, num_i32):
     m, p, c = voxels.shape
     out = torch.empty((m, c), dtype=torch.float32, device=voxels.device)
     check(lib().dz_mean_vfe(_p(_f32c(voxels)), _p(num_i32), m, p, c, _p(out), _stream()), 'mean_vfe')
+    _count(1)
     return out
 
 
@@ -105,6 +134,7 @@ def voxelize_dynamic_mean(points, c, B, pc_range, voxel_size, grid_xyz, cap):
     check(lib().dz_voxelize_dynamic_mean(_p(points), n, c, B, farr(pc_range), farr(voxel_size), iarr(grid_xyz),
                                          _p(feats), _p(coords), cap, _p(d_m), _p(ws), ws.numel(), _stream()),
           'voxelize_dynamic_mean')
+    _count(6)
     return feats, coords, d_m
 
 
@@ -113,6 +143,7 @@ def rulebook_subm(coords, d_n, cap, index, ksize):
     nbr = torch.empty((K, cap), dtype=torch.int32, device=coords.device)
     check(lib().dz_rulebook_subm(_p(coords), _p(d_n), cap, index.B, *index.dhw, iarr(ksize), _p(index.bitmap),
                                  _p(index.prefix), _p(index.perm), _p(nbr), _stream()), 'rulebook_subm')
+    _count(1)
     return nbr
 
 
@@ -133,19 +164,32 @@ def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap):
                                  iarr(pad), _p(in_index.bitmap), _p(in_index.prefix), _p(in_index.perm), _p(out_coords),
                                  _p(d_n_out), out_cap, _p(out_index.bitmap), _p(out_index.prefix), _p(nbr), _p(ws),
                                  ws.numel(), _stream()), 'rulebook_conv')
+    _count(6)
     return out_coords, d_n_out, out_index, nbr, out_dhw
 
 
-def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None):
+def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None,
+               d_n_in=None):
     """feats (in_cap, cin); nbr (K, nbr_cap); weight_packed (K, cin, cout)"""
     _need_cuda(feats, nbr, weight_packed)
     K, cin, cout = weight_packed.shape
     assert feats.shape[1] == cin and nbr.shape[0] == K
     if out is None:
         out = torch.empty((out_cap, cout), dtype=torch.float32, device=feats.device)
+    if _trace is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, _p(nbr), K, nbr.shape[1], _p(d_n_out), out_cap,
                               _p(_f32c(weight_packed)), _p(scale), _p(shift), _p(residual), int(relu), _p(out), cout,
                               mode, _stream()), 'spconv_fwd')
+    _count(1)
+    if _trace is not None:
+        ev1.record()
+        torch.cuda.synchronize()
+        n_out = min(int(d_n_out.item()), out_cap)
+        n_in = min(int(d_n_in.item()), feats.shape[0]) if d_n_in is not None else n_out
+        _trace.append(dict(start=ev0, end=ev1, K=K, cin=cin, cout=cout, n_in=n_in, n_out=n_out, nbr=nbr,
+                           residual=residual is not None))
     return out
 
 
@@ -157,15 +201,17 @@ def sparse_to_bev(feats, coords, d_n, cap, B, D, H, W, out=None):
         out.zero_()
     check(lib().dz_sparse_to_bev(_p(_f32c(feats)), _p(coords), _p(d_n), cap, c, B, D, H, W, _p(out), _stream()),
           'sparse_to_bev')
+    _count(1)
     return out
 
 
-def conv2d(x, weight_packed, stride, pad, scale, shift, relu, out=None, out_coff=0, mode=_lib.DZ_F32):
-    """x (B,H,W,cin) NHWC (may be a channel-slice view's base with in_cstride); weight (KH,KW,cin,cout)"""
+def conv2d(x, weight_packed, kshape, stride, pad, scale, shift, relu, out=None, out_coff=0, mode=_lib.DZ_F32):
+    """x (B,H,W,cin) NHWC; kshape = (KH, KW, cin, cout); weight_packed layout depends on mode:
+    DZ_F32 -> (KH,KW,cin,cout) ; DZ_TF32 -> (cout,KH,KW,cin)   (see pack_conv_weight)"""
     _need_cuda(x, weight_packed)
     B, H, W, cstride = x.shape
-    KH, KW, cin, cout = weight_packed.shape
-    assert cin == cstride
+    KH, KW, cin, cout = kshape
+    assert cin == cstride and weight_packed.numel() == KH * KW * cin * cout
     Ho = (H + 2 * pad - KH) // stride + 1
     Wo = (W + 2 * pad - KW) // stride + 1
     if out is None:
@@ -174,19 +220,36 @@ def conv2d(x, weight_packed, stride, pad, scale, shift, relu, out=None, out_coff
     check(lib().dz_conv2d_fwd(_p(_f32c(x)), B, H, W, cin, cstride, _p(_f32c(weight_packed)), KH, KW, stride, pad,
                               _p(scale), _p(shift), int(relu), _p(out), Ho, Wo, cout, out_coff, out.shape[3], mode,
                               _stream()), 'conv2d_fwd')
+    _count(1)
     return out
 
 
-def deconv2d(x, weight_packed, scale, shift, relu, out=None, out_coff=0, mode=_lib.DZ_F32):
-    """ConvTranspose2d with kernel == stride; weight (s,s,cin,cout)"""
+def deconv2d(x, weight_packed, kshape, scale, shift, relu, out=None, out_coff=0, mode=_lib.DZ_F32):
+    """ConvTranspose2d with kernel == stride; kshape = (s, cin, cout); weight layout DZ_F32 -> (s,s,cin,cout),
+    DZ_TF32 -> (s,s,cout,cin)"""
     B, H, W, cin = x.shape
-    s, s2, cin2, cout = weight_packed.shape
-    assert s == s2 and cin2 == cin
+    s, cin2, cout = kshape
+    assert cin2 == cin and weight_packed.numel() == s * s * cin * cout
     if out is None:
         out = torch.empty((B, H * s, W * s, cout), dtype=torch.float32, device=x.device)
     check(lib().dz_deconv2d_fwd(_p(_f32c(x)), B, H, W, cin, _p(_f32c(weight_packed)), s, _p(scale), _p(shift),
                                 int(relu), _p(out), cout, out_coff, out.shape[3], mode, _stream()), 'deconv2d_fwd')
+    _count(s * s)
     return out
+
+
+def pack_conv_weight(w_oihw, mode):
+    """torch (Cout,Cin,KH,KW) -> kernel layout for `mode`"""
+    if mode == _lib.DZ_F32:
+        return w_oihw.detach().permute(2, 3, 1, 0).contiguous().float()       # (KH,KW,Cin,Cout)
+    return w_oihw.detach().permute(0, 2, 3, 1).contiguous().float()           # (Cout,KH,KW,Cin): K-major rows for TMA
+
+
+def pack_deconv_weight(w_iohw, mode):
+    """torch ConvTranspose2d (Cin,Cout,s,s) -> kernel layout for `mode`"""
+    if mode == _lib.DZ_F32:
+        return w_iohw.detach().permute(2, 3, 0, 1).contiguous().float()       # (s,s,Cin,Cout)
+    return w_iohw.detach().permute(2, 3, 1, 0).contiguous().float()           # (s,s,Cout,Cin)
 
 
 def centerhead_decode(head, ch_layout, num_class, K, pc_range, voxel_size, fmap_stride, post_limit, score_thresh,
@@ -205,6 +268,7 @@ def centerhead_decode(head, ch_layout, num_class, K, pc_range, voxel_size, fmap_
                                      num_class, K, farr(pc_range), farr(voxel_size), int(fmap_stride), farr(post_limit),
                                      float(score_thresh), int(use_iou), _p(boxes), _p(scores), _p(labels), _p(d_n),
                                      _p(ws), ws.numel(), _stream()), 'centerhead_decode')
+    _count(2)
     return boxes, scores, labels, d_n
 
 
@@ -217,6 +281,7 @@ def nms_bev(boxes, scores, labels, d_n, thresh, post_max, label_offset=1):
     ws = workspace(lib().dz_nms_bev_ws_bytes(B, cap), dev, 'nms')
     check(lib().dz_nms_bev(_p(_f32c(boxes)), _p(_f32c(scores)), _p(labels), _p(d_n), B, cap, float(thresh), post_max,
                            label_offset, _p(out), _p(d_out_n), _p(ws), ws.numel(), _stream()), 'nms_bev')
+    _count(2)
     return out, d_out_n
 
 
@@ -226,6 +291,7 @@ def boxes_iou_bev(a, b):
     b = b[:, :7].contiguous().float()
     out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
     check(lib().dz_boxes_iou_bev(_p(a), a.shape[0], _p(b), b.shape[0], _p(out), _stream()), 'boxes_iou_bev')
+    _count(1)
     return out
 
 
@@ -240,6 +306,7 @@ def linear(x, w, scale=None, shift=None, relu=False, out=None, mode=_lib.DZ_F32)
     ldy = out.stride(0)
     check(lib().dz_linear_fwd(_p(_f32c(x)), M, K, _p(_f32c(w)), N, _p(scale), _p(shift), int(relu), _p(out), ldy, mode,
                               _stream()), 'linear_fwd')
+    _count(1)
     return out
 
 
@@ -248,6 +315,7 @@ def group_max(x, G, group):
     assert x.shape[0] == G * group
     y = torch.empty((G, C), dtype=torch.float32, device=x.device)
     check(lib().dz_group_max(_p(_f32c(x)), G, group, C, _p(y), _stream()), 'group_max')
+    _count(1)
     return y
 
 
@@ -262,6 +330,7 @@ def attention(q, k, v, key_padding_mask, H, mode=_lib.DZ_F32):
     out = torch.empty((B, Pq, E), dtype=torch.float32, device=q.device)
     check(lib().dz_attention_fwd(_p(q), q.stride(1), _p(k), k.stride(1), _p(v), v.stride(1), _p(key_padding_mask), B, Pq,
                                  Pk, H, dh, _p(out), E, mode, _stream()), 'attention_fwd')
+    _count(1)
     return out
 
 
@@ -270,4 +339,13 @@ def layernorm_residual(x, r, gamma, beta, eps=1e-5):
     y = torch.empty_like(x)
     check(lib().dz_layernorm_residual(_p(_f32c(x)), _p(r), _p(gamma), _p(beta), float(eps), M, C, _p(y), _stream()),
           'layernorm_residual')
+    _count(1)
     return y
+
+
+def add(a, b):
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    check(lib().dz_add(_p(a), _p(b), a.numel(), _p(out), _stream()), 'add')
+    _count(1)
+    return out

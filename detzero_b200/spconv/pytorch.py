@@ -197,7 +197,7 @@ class _SparseConv(SparseModule):
                                  None if residual is None else residual._feat, relu, mode)
             return x._like(out)
         out = ops.spconv_fwd(x._feat, rule.nbr, rule.d_n_out, rule.out_cap, self.packed_weight(), scale, shift, None,
-                             relu, mode)
+                             relu, mode, d_n_in=x._count)
         return SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
                                 count=rule.d_n_out, n_host=None, index=rule.out_index)
 

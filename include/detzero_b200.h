@@ -167,6 +167,9 @@ int dz_attention_fwd(const float* q, int ldq, const float* k, int ldk, const flo
 int dz_layernorm_residual(const float* x, const float* r, const float* gamma, const float* beta, float eps,
                           int M, int C, float* y, dz_stream_t stream);
 
+/* out = a + b, n % 4 == 0 (with_pos_embed, decoder.py:45-46) */
+int dz_add(const float* a, const float* b, size_t n, float* out, dz_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@ import torch
 import oracle
 from oracle import det_ref, spconv_ref, weights
 from tests import util
+from detzero_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -174,9 +175,12 @@ def test_conv2d_fp32(cuda, cin, cout, k, stride, pad, H, W):
     w = torch.randn(cout, cin, k, k, generator=g) * 0.05
     scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
     ref = torch.relu(torch.nn.functional.conv2d(x, w, None, stride, pad) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
-    out = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), w.permute(2, 3, 1, 0).contiguous().to(cuda), stride, pad,
-                     scale.to(cuda), shift.to(cuda), True)
-    assert util.rel_err(out.permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+    for mode, tol in ((_lib.DZ_F32, 1e-5), (_lib.DZ_TF32, 2e-3)):
+        if mode == _lib.DZ_TF32 and cin % 32:
+            continue
+        out = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), ops.pack_conv_weight(w, mode).to(cuda), (k, k, cin, cout),
+                         stride, pad, scale.to(cuda), shift.to(cuda), True, mode=mode)
+        assert util.rel_err(out.permute(0, 3, 1, 2).cpu(), ref) < tol, mode
 
 
 @pytest.mark.parametrize('s', [1, 2])
@@ -186,11 +190,12 @@ def test_deconv2d_fp32_concat(cuda, s):
     x = torch.randn(2, 64, 7, 9, generator=g)
     w = torch.randn(64, 32, s, s, generator=g) * 0.1
     ref = torch.nn.functional.conv_transpose2d(x, w, None, stride=s)
-    out = torch.zeros(2, 7 * s, 9 * s, 48, device=cuda)
-    ops.deconv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), w.permute(2, 3, 0, 1).contiguous().to(cuda), None, None, False,
-                 out=out, out_coff=16)
-    assert util.rel_err(out[..., 16:].permute(0, 3, 1, 2).cpu(), ref) < 1e-5
-    assert out[..., :16].abs().max().item() == 0
+    for mode, tol in ((_lib.DZ_F32, 1e-5), (_lib.DZ_TF32, 2e-3)):
+        out = torch.zeros(2, 7 * s, 9 * s, 48, device=cuda)
+        ops.deconv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), ops.pack_deconv_weight(w, mode).to(cuda), (s, 64, 32), None, None,
+                     False, out=out, out_coff=16, mode=mode)
+        assert util.rel_err(out[..., 16:].permute(0, 3, 1, 2).cpu(), ref) < tol, mode
+        assert out[..., :16].abs().max().item() == 0
 
 
 def test_sparse_to_bev(cuda):
