@@ -40,7 +40,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--backbone', default='VoxelBackBone8x', choices=['VoxelBackBone8x', 'VoxelResBackBone8x'])
-    ap.add_argument('--mode', default=os.environ.get('DZ_MODE', 'fp32'), help='fp32 | tf32 | bf16 (dense BEV convs)')
+    ap.add_argument('--mode', default=os.environ.get('DZ_MODE', 'tf32'),
+                    help='dense BEV/head convs: tf32 (tcgen05; what the reference gets from cuDNN by default, SURVEY A.6) | fp32 (exact FMA)')
     ap.add_argument('--sp-mode', default=os.environ.get('DZ_SP_MODE', 'fp32'), help='sparse-conv arithmetic')
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')

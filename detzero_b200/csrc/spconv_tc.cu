@@ -1,0 +1,239 @@
+// spconv_tc.cu -- sparse convolution forward on the 5th-gen tensor cores (tcgen05, TF32 operands, fp32 TMEM accumulators).
+//
+// Same contract as the exact-fp32 kernel in spconv.cu (SubMConv3d / SparseConv3d + folded BatchNorm1d + bias + residual
+// + ReLU, backbone3d.py:64-83,105-121) for DZ_TF32.  spconv's own default keeps TF32 off, so this mode
+// is opt-in (COMPUTE_MODE: tf32) with a stated 2e-3 tolerance.
+//
+// Design: output-stationary implicit GEMM.  A CTA owns 128 consecutive output rows; the reduction dimension is the
+// concatenation (kernel offset k, input channel c) of length K*Cin, cut into 32-float (128-byte) blocks -- for
+// Cin = 16 one block spans two offsets, for Cin = 64 an offset spans two blocks -- so narrow layers still fill the
+// MMA K dimension.  Per block, 4 producer warps gather the neighbour rows straight from global/L2 into shared memory
+// with cp.async (zero-fill for missing neighbours) in the canonical K-major 128B-swizzled UMMA layout, one thread
+// TMA-loads the matching W[cout][k-block] tile, and one thread issues tcgen05.mma (M=128, N=Cout, K=8) into TMEM.
+// Blocks whose offsets have no neighbour anywhere in the tile are skipped.  The producers then become the epilogue:
+// tcgen05.ld -> scale/shift (+residual) -> ReLU -> 128-bit stores.  No atomics: deterministic.
+#include "common.cuh"
+#include "tc.cuh"
+
+static constexpr int ST_ROWS = 128;
+static constexpr int ST_A_BYTES = ST_ROWS * 128;        // one 32-float block for 128 rows
+static constexpr int ST_THREADS = 160;                  // warps 0-3 gather + epilogue, warp 4 MMA / TMEM
+static constexpr int ST_KMAX = 27;
+
+template <int COUT>
+struct StCfg {
+    static constexpr int W_BYTES = COUT * 128;
+    static constexpr int STAGE_BYTES = ST_A_BYTES + W_BYTES;
+    static constexpr int STAGES = 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + ST_KMAX * ST_ROWS * 4 + 128 * 4 + 256;
+    static constexpr int TMEM_COLS = COUT < 32 ? 32 : COUT;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool valid) {
+    int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+template <int CIN_PAD, int COUT>
+__global__ void __launch_bounds__(ST_THREADS)
+k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ in, int cin, const int32_t* __restrict__ nbr, int K,
+              int nbr_cap, const int* __restrict__ d_n_out, int out_cap, const float* __restrict__ scale,
+              const float* __restrict__ shift, const float* __restrict__ residual, int relu, float* __restrict__ out) {
+    using Cfg = StCfg<COUT>;
+    const int n = min(*d_n_out, out_cap);
+    const int row0 = blockIdx.x * ST_ROWS;
+    if (row0 >= n) return;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    int* s_nbr = reinterpret_cast<int*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);          // [K][128]
+    int* s_blocks = s_nbr + ST_KMAX * ST_ROWS;                                            // active block list (<= 108)
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_blocks + 124);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tmem_full = empty + Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    int* s_nb = reinterpret_cast<int*>(tmem_slot + 1);
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_nb + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ktot = K * CIN_PAD;
+    const int nb_tot = (ktot + 31) / 32;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmW);
+        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full + s, ST_ROWS + 1); tc::mbar_init(empty + s, 1); }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+        *s_mask = 0u;
+    }
+    if (warp == 4) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    __syncthreads();
+    // ---- neighbour rows of this tile + which offsets are populated
+    if (warp < 4) {
+        const int r = row0 + threadIdx.x;
+        for (int k = 0; k < K; ++k) {
+            int v = r < n ? __ldg(nbr + (size_t)k * nbr_cap + r) : -1;
+            s_nbr[k * ST_ROWS + threadIdx.x] = v;
+            unsigned bal = __ballot_sync(0xffffffffu, v >= 0);
+            if (lane == 0 && bal) atomicOr(s_mask, 1u << k);
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    if (threadIdx.x == 0) {
+        const unsigned mask = *s_mask;
+        int nb = 0;
+        for (int kb = 0; kb < nb_tot; ++kb) {
+            int k_lo = (kb * 32) / CIN_PAD, k_hi = min(K - 1, (kb * 32 + 31) / CIN_PAD);
+            bool act = false;
+            for (int k = k_lo; k <= k_hi; ++k) act |= (mask >> k) & 1u;
+            if (act) s_blocks[nb++] = kb;
+        }
+        *s_nb = nb;
+    }
+    __syncthreads();
+    const int nb = *s_nb;
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ================= producers: gather A blocks (cp.async) + TMA for W =================
+        const int j = threadIdx.x & 7;              // 16-byte chunk inside the 128-byte row
+        const int rbase = threadIdx.x >> 3;         // rows rbase + 16*i
+        for (int it = 0; it < nb; ++it) {
+            const int s = it % Cfg::STAGES;
+            const int kb = s_blocks[it];
+            tc::mbar_wait(empty + s, ((it / Cfg::STAGES) & 1) ^ 1);
+            unsigned char* sa = smem + s * Cfg::STAGE_BYTES;
+            const uint32_t sa_u = tc::smem_u32(sa);
+            if (threadIdx.x == 0) {
+                tc::mbar_arrive_expect_tx(full + s, Cfg::W_BYTES);
+                tc::tma_load_2d(sa + ST_A_BYTES, &tmW, full + s, kb * 32, 0);
+            }
+            const int kidx = kb * 32 + j * 4;       // position in the concatenated (offset, channel) dimension
+            const int k = kidx / CIN_PAD, c = kidx % CIN_PAD;
+            const bool k_ok = k < K;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                const int src_row = k_ok ? s_nbr[k * ST_ROWS + r] : -1;
+                const uint32_t dst = sa_u + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+                if (CIN_PAD >= 16) {
+                    const bool ok = src_row >= 0;
+                    cp_async16_zfill(dst, ok ? (const void*)(in + (size_t)src_row * cin + c) : (const void*)in, ok);
+                } else {
+                    // first layer (cin = 5 padded to 8): rows are not 16-byte aligned -> 4-byte copies
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool ok = src_row >= 0 && (c + e) < cin;
+                        cp_async4_zfill(dst + 4 * e, ok ? (const void*)(in + (size_t)src_row * cin + c + e) : (const void*)in, ok);
+                    }
+                }
+            }
+            cp_async_mbar_arrive_noinc(full + s);
+        }
+        // ================= epilogue =================
+        const int q = warp;                         // TMEM lane quarter == warp id for warps 0..3
+        const int r = row0 + q * 32 + lane;
+        tc::mbar_wait(tmem_full, 0);
+        tc::tcgen05_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (r < n) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4) {
+                    const int ch = c0 + jj;
+                    if (ch >= COUT) break;
+                    float4 o = nb > 0 ? make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (scale) { float4 sc = __ldg(reinterpret_cast<const float4*>(scale + ch)); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+                    if (shift) { float4 sh = __ldg(reinterpret_cast<const float4*>(shift + ch)); o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w; }
+                    if (residual) {
+                        float4 rr = __ldg(reinterpret_cast<const float4*>(residual + (size_t)r * COUT + ch));
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(out + (size_t)r * COUT + ch) = o;
+                }
+            }
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::instr_desc(2, 128, COUT);
+            for (int it = 0; it < nb; ++it) {
+                const int s = it % Cfg::STAGES;
+                tc::mbar_wait(full + s, (it / Cfg::STAGES) & 1);
+                tc::fence_proxy_async();                  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+                tc::tcgen05_fence_after();
+                const uint32_t sa = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint64_t adesc = tc::smem_desc_sw128(sa), bdesc = tc::smem_desc_sw128(sa + ST_A_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    tc::mma_tf32(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (it | kk) ? 1u : 0u);
+                tc::mma_commit(empty + s);
+            }
+            tc::mma_commit(tmem_full);
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int CIN_PAD, int COUT>
+static int launch(const CUtensorMap& tmW, const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
+                  int out_cap, const float* scale, const float* shift, const float* residual, int relu, float* out, cudaStream_t st) {
+    using Cfg = StCfg<COUT>;
+    static bool configured = false;
+    if (!configured) {
+        DZ_CUDA(cudaFuncSetAttribute(k_spconv_tf32<CIN_PAD, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        configured = true;
+    }
+    k_spconv_tf32<CIN_PAD, COUT><<<dz_cdiv(out_cap, ST_ROWS), ST_THREADS, Cfg::SMEM, st>>>(tmW, in, cin, nbr, K, nbr_cap, d_n_out, out_cap,
+                                                                                          scale, shift, residual, relu, out);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
+}
+
+// weight layout for this path: (cout, K * cin_pad) row-major, cin_pad = 8 for cin <= 8 else cin
+int dz_spconv_fwd_tc(const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out, int out_cap,
+                     const float* weight, const float* scale, const float* shift, const float* residual, int relu, float* out,
+                     int cout, int mode, cudaStream_t st) {
+    if (mode != DZ_TF32) { dz_set_error("dz_spconv_fwd: tensor-core mode %d not built (tf32 only)", mode); return DZ_ERR_UNSUPPORTED; }
+    if (K > ST_KMAX) { dz_set_error("dz_spconv_fwd(tf32): K=%d > 27", K); return DZ_ERR_UNSUPPORTED; }
+    const int cin_pad = cin <= 8 ? 8 : cin;
+    tc::EncodeTiledFn enc = tc::get_encode_tiled();
+    if (!enc) { dz_set_error("cuTensorMapEncodeTiled unavailable"); return DZ_ERR_CUDA; }
+    CUtensorMap tmW;
+    {
+        cuuint64_t ktot = (cuuint64_t)K * cin_pad;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {ktot * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)cout};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)weight, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(W) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
+#define DZ_ST(CP, CO) return launch<CP, CO>(tmW, in, cin, nbr, K, nbr_cap, d_n_out, out_cap, scale, shift, residual, relu, out, st)
+    if (cin_pad == 8 && cout == 16) DZ_ST(8, 16);
+    if (cin_pad == 16 && cout == 16) DZ_ST(16, 16);
+    if (cin_pad == 16 && cout == 32) DZ_ST(16, 32);
+    if (cin_pad == 32 && cout == 32) DZ_ST(32, 32);
+    if (cin_pad == 32 && cout == 64) DZ_ST(32, 64);
+    if (cin_pad == 64 && cout == 64) DZ_ST(64, 64);
+    if (cin_pad == 64 && cout == 128) DZ_ST(64, 128);
+    if (cin_pad == 128 && cout == 128) DZ_ST(128, 128);
+#undef DZ_ST
+    dz_set_error("dz_spconv_fwd(tf32): (cin=%d, cout=%d) not instantiated", cin, cout);
+    return DZ_ERR_UNSUPPORTED;
+}

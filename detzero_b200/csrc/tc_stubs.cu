@@ -2,10 +2,6 @@
 // fallback to the fp32 path.
 #include "common.cuh"
 
-int dz_spconv_fwd_tc(const float*, int, const int32_t*, int, int, const int*, int, const float*, const float*, const float*,
-                     const float*, int, float*, int, int mode, cudaStream_t) {
-    dz_set_error("dz_spconv_fwd: tensor-core mode %d not built", mode); return DZ_ERR_UNSUPPORTED;
-}
 int dz_linear_fwd_tc(const float*, int, int, const float*, int, const float*, const float*, int, float*, int, int mode, cudaStream_t) {
     dz_set_error("dz_linear_fwd: tensor-core mode %d not built", mode); return DZ_ERR_UNSUPPORTED;
 }

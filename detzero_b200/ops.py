@@ -168,11 +168,24 @@ def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap):
     return out_coords, d_n_out, out_index, nbr, out_dhw
 
 
+def pack_spconv_weight(w, mode):
+    """spconv-2.x parameter (Cout, KD, KH, KW, Cin) -> kernel layout: DZ_F32 (K, Cin, Cout); DZ_TF32 (Cout, K*cin_pad)
+    with cin_pad = 8 for Cin <= 8 (the reduction dim is the concatenation (offset, channel), 128-byte blocks)"""
+    cout, cin = w.shape[0], w.shape[-1]
+    w = w.detach().reshape(cout, -1, cin).float()
+    if mode == _lib.DZ_F32:
+        return w.permute(1, 2, 0).contiguous()
+    cin_pad = 8 if cin <= 8 else cin
+    if cin_pad != cin:
+        w = torch.nn.functional.pad(w, (0, cin_pad - cin))
+    return w.reshape(cout, -1).contiguous()
+
+
 def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None,
-               d_n_in=None):
-    """feats (in_cap, cin); nbr (K, nbr_cap); weight_packed (K, cin, cout)"""
+               d_n_in=None, kshape=None):
+    """feats (in_cap, cin); nbr (K, nbr_cap); weight_packed per pack_spconv_weight; kshape = (K, cin, cout)"""
     _need_cuda(feats, nbr, weight_packed)
-    K, cin, cout = weight_packed.shape
+    K, cin, cout = kshape if kshape is not None else weight_packed.shape
     assert feats.shape[1] == cin and nbr.shape[0] == K
     if out is None:
         out = torch.empty((out_cap, cout), dtype=torch.float32, device=feats.device)

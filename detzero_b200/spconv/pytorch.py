@@ -162,14 +162,17 @@ class _SparseConv(SparseModule):
         self._packed = None
         self._packed_ver = None
 
-    def packed_weight(self):
-        """(K, Cin, Cout) contiguous copy of the spconv-layout parameter (refreshed when the parameter changes)"""
-        ver = (self.weight._version, self.weight.data_ptr())
+    def packed_weight(self, mode=_lib.DZ_F32):
+        """kernel-layout copy of the spconv-layout parameter (refreshed when the parameter changes)"""
+        ver = (self.weight._version, self.weight.data_ptr(), mode)
         if self._packed is None or self._packed_ver != ver:
-            w = self.weight.detach()
-            self._packed = w.reshape(self.out_channels, -1, self.in_channels).permute(1, 2, 0).contiguous().float()
+            self._packed = ops.pack_spconv_weight(self.weight, mode)
             self._packed_ver = ver
         return self._packed
+
+    @property
+    def kshape(self):
+        return (self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2], self.in_channels, self.out_channels)
 
     def _rule(self, x):
         key = self.indice_key
@@ -193,11 +196,11 @@ class _SparseConv(SparseModule):
         rule = self._rule(x)
         mode = _lib.MODES[self.mode]
         if self.subm:
-            out = ops.spconv_fwd(x._feat, rule.nbr, x._count, x._cap, self.packed_weight(), scale, shift,
-                                 None if residual is None else residual._feat, relu, mode)
+            out = ops.spconv_fwd(x._feat, rule.nbr, x._count, x._cap, self.packed_weight(mode), scale, shift,
+                                 None if residual is None else residual._feat, relu, mode, kshape=self.kshape)
             return x._like(out)
-        out = ops.spconv_fwd(x._feat, rule.nbr, rule.d_n_out, rule.out_cap, self.packed_weight(), scale, shift, None,
-                             relu, mode, d_n_in=x._count)
+        out = ops.spconv_fwd(x._feat, rule.nbr, rule.d_n_out, rule.out_cap, self.packed_weight(mode), scale, shift, None,
+                             relu, mode, d_n_in=x._count, kshape=self.kshape)
         return SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
                                 count=rule.d_n_out, n_host=None, index=rule.out_index)
 
