@@ -24,7 +24,8 @@ template <int COUT>
 struct StCfg {
     static constexpr int W_BYTES = COUT * 128;
     static constexpr int STAGE_BYTES = ST_A_BYTES + W_BYTES;
-    static constexpr int STAGES = 4;
+    // 2 CTAs/SM for COUT <= 64 (the other CTA's prologue/epilogue overlaps this one's main loop), 1 CTA/SM for 128
+    static constexpr int STAGES = COUT >= 128 ? 6 : 4;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + ST_KMAX * ST_ROWS * 4 + 128 * 4 + 256;
     static constexpr int TMEM_COLS = COUT < 32 ? 32 : COUT;
 };
@@ -78,12 +79,18 @@ k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__
     // ---- neighbour rows of this tile + which offsets are populated
     if (warp < 4) {
         const int r = row0 + threadIdx.x;
-        for (int k = 0; k < K; ++k) {
-            int v = r < n ? __ldg(nbr + (size_t)k * nbr_cap + r) : -1;
-            s_nbr[k * ST_ROWS + threadIdx.x] = v;
-            unsigned bal = __ballot_sync(0xffffffffu, v >= 0);
-            if (lane == 0 && bal) atomicOr(s_mask, 1u << k);
+        int v[ST_KMAX];
+#pragma unroll
+        for (int k = 0; k < ST_KMAX; ++k)              // all loads in flight at once (k-major table: coalesced)
+            v[k] = (k < K && r < n) ? __ldg(nbr + (size_t)k * nbr_cap + r) : -1;
+        unsigned mine = 0;
+#pragma unroll
+        for (int k = 0; k < ST_KMAX; ++k) {
+            if (k < K) s_nbr[k * ST_ROWS + threadIdx.x] = v[k];
+            mine |= (v[k] >= 0 ? 1u : 0u) << k;
         }
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if (lane == 0 && mine) atomicOr(s_mask, mine);
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -161,6 +168,8 @@ k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__
                         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                     }
                     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    // round-to-nearest to TF32: the next layer's truncating tensor-core read is then exact (no toward-zero bias)
+                    o.x = tc::rna_tf32(o.x); o.y = tc::rna_tf32(o.y); o.z = tc::rna_tf32(o.z); o.w = tc::rna_tf32(o.w);
                     *reinterpret_cast<float4*>(out + (size_t)r * COUT + ch) = o;
                 }
             }

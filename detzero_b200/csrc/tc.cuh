@@ -100,6 +100,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 // ---- descriptors ------------------------------------------------------------------------------------------------
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (tile base 1024 B aligned).
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {

@@ -362,10 +362,11 @@ __global__ void __launch_bounds__(VOX_THREADS) k_vox_write(const float* __restri
 
 __global__ void k_vox_finish(const int* __restrict__ d_tmp, int max_voxels, int cap, int* __restrict__ d_counters) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int nv = min(d_tmp[1], max_voxels);
-        nv = min(nv, cap - d_counters[0]);
+        int want = min(d_tmp[1], max_voxels);
+        int nv = min(want, cap - d_counters[0]);
         d_counters[0] += nv;
         d_counters[1] = d_tmp[0];
+        d_counters[2] += want;          // rows the caller's capacity should have held (== [0] unless cap was too small)
     }
 }
 

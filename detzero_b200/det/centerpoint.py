@@ -91,12 +91,13 @@ class CenterPoint(nn.Module):
         levels = [t for t in batch_dict.get('multi_scale_3d_features', {}).values()] + \
                  [batch_dict.get('encoded_spconv_tensor')]
         levels = [t for t in levels if t is not None and t._n is None]
-        flat = torch.cat([counts.flatten()] + [t._count for t in levels]).tolist()
+        vw = batch_dict.get('voxel_wanted')
+        flat = torch.cat([counts.flatten()] + [t._count for t in levels] + ([vw[0]] if vw is not None else [])).tolist()
         nb = counts.numel()
+        if vw is not None:
+            vw[2].note_count(int(flat[-1]), vw[1])
         for t, n in zip(levels, flat[nb:]):
-            if n > t._cap:
-                raise RuntimeError('sparse level overflow: %d sites > capacity %d' % (n, t._cap))
-            t._n = int(n)
+            t.set_num(int(n))                              # raises on overflow, updates the layer capacity hints
         shaped = torch.tensor(flat[:nb]).view(counts.shape)
         pred_dicts = dense.CenterHead.boxes_to_dicts(batch_dict['final_boxes_padded'], shaped)
         batch_dict['final_box_dicts'] = pred_dicts

@@ -61,6 +61,7 @@ class MeanVFE(nn.Module):
         batch_dict['voxel_features'] = r['mean']
         batch_dict['voxel_count'] = r['counters'][0:1]           # device scalar: true number of rows
         batch_dict['voxel_grid_index'] = r['index']
+        batch_dict['voxel_wanted'] = (r['counters'][2:3], r['cap'], gen)      # checked in CenterPoint.post_processing
         return batch_dict
 
 

@@ -178,7 +178,15 @@ def pack_spconv_weight(w, mode):
     cin_pad = 8 if cin <= 8 else cin
     if cin_pad != cin:
         w = torch.nn.functional.pad(w, (0, cin_pad - cin))
-    return w.reshape(cout, -1).contiguous()
+    return round_tf32(w.reshape(cout, -1).contiguous())
+
+
+def round_tf32(t):
+    """round-to-nearest-even to TF32 precision (10 explicit mantissa bits) so the tensor core's truncating read of the
+    fp32 container is exact: removes the systematic toward-zero bias of truncation"""
+    i = t.contiguous().view(torch.int32)
+    lsb = (i >> 13) & 1
+    return ((i + 0xFFF + lsb) & ~0x1FFF).view(torch.float32)
 
 
 def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None,
@@ -255,14 +263,14 @@ def pack_conv_weight(w_oihw, mode):
     """torch (Cout,Cin,KH,KW) -> kernel layout for `mode`"""
     if mode == _lib.DZ_F32:
         return w_oihw.detach().permute(2, 3, 1, 0).contiguous().float()       # (KH,KW,Cin,Cout)
-    return w_oihw.detach().permute(0, 2, 3, 1).contiguous().float()           # (Cout,KH,KW,Cin): K-major rows for TMA
+    return round_tf32(w_oihw.detach().permute(0, 2, 3, 1).contiguous().float())   # (Cout,KH,KW,Cin): K-major rows for TMA
 
 
 def pack_deconv_weight(w_iohw, mode):
     """torch ConvTranspose2d (Cin,Cout,s,s) -> kernel layout for `mode`"""
     if mode == _lib.DZ_F32:
         return w_iohw.detach().permute(2, 3, 0, 1).contiguous().float()       # (s,s,Cin,Cout)
-    return w_iohw.detach().permute(2, 3, 1, 0).contiguous().float()           # (s,s,Cout,Cin)
+    return round_tf32(w_iohw.detach().permute(2, 3, 1, 0).contiguous().float())   # (s,s,Cout,Cin)
 
 
 def centerhead_decode(head, ch_layout, num_class, K, pc_range, voxel_size, fmap_stride, post_limit, score_thresh,

@@ -51,11 +51,17 @@ class SparseConvTensor:
     def num(self):
         """true number of rows (host int); one device->host read the first time if it is not known yet"""
         if self._n is None:
-            n = int(self._count.item())
-            if n > self._cap:
-                raise RuntimeError('sparse tensor overflow: %d sites > capacity %d (raise the capacity factor)' % (n, self._cap))
-            self._n = n
+            self.set_num(int(self._count.item()))
         return self._n
+
+    def set_num(self, n):
+        """record the true row count (read back by the caller); feeds the producing layer's capacity hint"""
+        prod = getattr(self, '_producer', None)
+        if prod is not None:
+            prod._cap_hint = max(n, int(getattr(prod, '_cap_hint', 0) or 0))
+        if n > self._cap:
+            raise RuntimeError('sparse tensor overflow: %d sites > capacity %d (capacity hint raised; re-run the frame)' % (n, self._cap))
+        self._n = n
 
     @property
     def features(self):
@@ -143,9 +149,12 @@ class _RuleConv:
 
 
 class _SparseConv(SparseModule):
-    #: capacity of a strided conv's output relative to its input capacity (k3 s2 sites grow by <= ~1.5x in practice,
-    #: 8x in theory); overflow is detected (device count > capacity) and raised, never silently truncated
+    #: capacity of a strided conv's output relative to its input capacity the FIRST time a layer runs (k3 s2 sites grow
+    #: by <= ~1.8x in practice, 8x in theory).  Afterwards the capacity follows the largest count this layer has produced
+    #: (x CAP_HEADROOM), so buffers and launch grids track the real sparsity without a per-frame host sync.  Overflow
+    #: is detected (device count > capacity), raised, and the hint grows -- never silently truncated.
     OUT_CAP_FACTOR = 3.0
+    CAP_HEADROOM = 1.3
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
                  indice_key=None, subm=False, algo=None, mode='fp32'):
@@ -186,6 +195,9 @@ class _SparseConv(SparseModule):
                 cells = x.batch_size * out_dhw[0] * out_dhw[1] * out_dhw[2]
                 grow = self.OUT_CAP_FACTOR if max(self.stride) > 1 and min(self.kernel_size) > 1 else 1.0
                 out_cap = int(min(cells, max(64, int(x._cap * grow))))
+                hint = getattr(self, '_cap_hint', None)
+                if hint is not None:
+                    out_cap = int(min(cells, max(128, (int(hint * self.CAP_HEADROOM) + 127) // 128 * 128)))
                 rule = _RuleConv(*_reorder(ops.rulebook_conv(x._idx, x._count, x._cap, in_index, self.kernel_size,
                                                               self.stride, self.padding, out_cap)), out_cap)
             if key is not None:
@@ -201,8 +213,10 @@ class _SparseConv(SparseModule):
             return x._like(out)
         out = ops.spconv_fwd(x._feat, rule.nbr, rule.d_n_out, rule.out_cap, self.packed_weight(mode), scale, shift, None,
                              relu, mode, d_n_in=x._count, kshape=self.kshape)
-        return SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
-                                count=rule.d_n_out, n_host=None, index=rule.out_index)
+        t = SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
+                             count=rule.d_n_out, n_host=None, index=rule.out_index)
+        t._producer = self
+        return t
 
     def forward(self, x):
         shift = None if self.bias is None else self.bias.detach().float()

@@ -31,18 +31,27 @@ class Point2VoxelGPU3d:
         device counters -- no host sync.  dict(voxels, coords[b,z,y,x], num, mean, counters, index, cap)"""
         B = len(clouds)
         cap = sum(min(int(c.shape[0]), self.max_voxels) for c in clouds)
+        hint = getattr(self, '_cap_hint', None)           # largest voxel count seen so far (set by the caller's read-back)
+        if hint is not None:
+            cap = min(cap, (int(hint * 1.3) + 127) // 128 * 128)
         cap = max(cap, 1)
         dev = clouds[0].device
         voxels = torch.empty((cap, self.max_pts, self.c), dtype=torch.float32, device=dev)
         coords = torch.zeros((cap, 4), dtype=torch.int32, device=dev)
         num = torch.zeros((cap,), dtype=torch.int32, device=dev)
         mean = torch.empty((cap, self.c), dtype=torch.float32, device=dev)
-        counters = torch.zeros(2, dtype=torch.int32, device=dev)
+        counters = torch.zeros(3, dtype=torch.int32, device=dev)
         index = ops.GridIndex(B, self.sparse_shape, dev, with_perm_cap=sum(int(c.shape[0]) for c in clouds) + 1)
         for b, pts in enumerate(clouds):
             ops.voxelize_hard(pts, xyz_off, self.c, self.range, self.vsize, self.grid_zyx, self.max_pts,
                               self.max_voxels, b, voxels, coords, num, mean, counters, index)
         return dict(voxels=voxels, coords=coords, num=num, mean=mean, counters=counters, index=index, cap=cap)
+
+    def note_count(self, wanted, cap):
+        """feed the read-back voxel count into the capacity hint; raises if the capacity truncated the frame"""
+        self._cap_hint = max(int(wanted), int(getattr(self, '_cap_hint', 0) or 0))
+        if wanted > cap:
+            raise RuntimeError('voxel capacity overflow: %d voxels > capacity %d (hint raised; re-run the frame)' % (wanted, cap))
 
     def point_to_voxel(self, points):
         """API-compatible single-cloud call: returns (voxels (M,P,C), coords (M,3) [z,y,x], num (M,)) CUDA tensors.
@@ -52,6 +61,7 @@ class Point2VoxelGPU3d:
         points = points.float().contiguous()
         r = self.voxelize_batch([points])
         m = int(r['counters'][0].item())
+        self.note_count(int(r['counters'][2].item()), r['cap'])
         return r['voxels'][:m], r['coords'][:m, 1:4].contiguous(), r['num'][:m]
 
 

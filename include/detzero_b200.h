@@ -54,7 +54,7 @@ int dz_grid_index_from_coords(const int32_t* coords, const int* d_n, int cap, in
  *   verbatim (xyz_off = 1 for a collated (N,1+C) [b,x,y,z,..] tensor, 0 for a raw (N,C) cloud)
  *   voxels (cap, max_pts, c) ; coords (cap,4) [batch_idx,z,y,x] ; num_per_voxel (cap) ; mean (cap,c) or NULL
  *   d_counters[0] = rows already used in voxels/coords (in/out), d_counters[1] = ranks already used in the
- *   index (in/out): calling once per frame with batch_idx = 0..B-1 on one stream builds a collated batch
+ *   index (in/out), d_counters[2] = rows wanted (in/out; > [0] iff `cap` was too small): calling once per frame with batch_idx = 0..B-1 on one stream builds a collated batch
  *   (dataset.py:260-303) without a host sync.
  *   index_* : level-0 grid index over lattice (B, iD, iH, iW) (iD = sparse_shape z = grid z + 1,
  *   backbone3d.py:133); bitmap must be zero before the first frame of a batch. */
