@@ -129,7 +129,7 @@ def run_reference(args):
     import torch
     if int(os.environ.get('RANK', '0')) != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     run = cpu_frame_fn(args.backbone)
     for i in range(args.warmup):
@@ -295,15 +295,21 @@ def sparse_conv_roofline(model, step_fn, args, dev):
             'algorithmic_bytes_per_frame': tot_bytes, 'algorithmic_flops_per_frame': tot_flops, 'ms_per_frame': tot_ms}
 
 
+def cpu_threads():
+    """threads the CPU arm uses: the oracle port (numpy rulebooks + torch gather/mm/index_add + oneDNN convs) stops scaling
+    -- and on a 128-core host gets ~30x SLOWER from oversubscription -- beyond ~16 threads"""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get('DZ_CPU_THREADS', '16'))))
+
+
 def cpu_baseline(args):
     import torch
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     run = cpu_frame_fn(args.backbone)
     run(0)
     t0 = time.perf_counter()
     n = 0
-    while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 8):
+    while n < 2 or (time.perf_counter() - t0 < 12.0 and n < 8):
         run(n)
         n += 1
     dt = time.perf_counter() - t0

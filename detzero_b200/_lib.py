@@ -33,7 +33,7 @@ _SIGS = {
     'dz_voxelize_dynamic_mean': (ci, [vp, ci, ci, ci, vp, vp, vp, vp, vp, ci, vp, vp, sz, vp]),
     'dz_rulebook_subm': (ci, [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
     'dz_rulebook_conv': (ci, [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, sz, vp]),
-    'dz_spconv_fwd': (ci, [vp, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, ci, vp]),
+    'dz_spconv_fwd': (ci, [vp, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, ci, vp]),
     'dz_sparse_to_bev': (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]),
     'dz_conv2d_fwd': (ci, [vp, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, vp]),
     'dz_deconv2d_fwd': (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, vp]),

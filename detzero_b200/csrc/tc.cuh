@@ -52,6 +52,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// gather4: four rows (given by index) of a 2-D tensor, box = {cols, 1}; lands as 4 consecutive box-rows at smem_dst.
+// Row indices outside the tensor are zero-filled.
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int col, int r0, int r1, int r2, int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------------------------
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {      // one full warp
@@ -115,6 +124,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+// K-major operand tile with 64-byte rows (16 fp32), 64-byte swizzle: 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                                // SWIZZLE_64B
     return d;
 }
 // instruction descriptor: fp32 accumulate, A and B K-major.  fmt: 0 = f16, 1 = bf16, 2 = tf32

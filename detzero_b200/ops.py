@@ -200,7 +200,7 @@ def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residu
     if _trace is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, _p(nbr), K, nbr.shape[1], _p(d_n_out), out_cap,
+    check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, feats.shape[0], _p(nbr), K, nbr.shape[1], _p(d_n_out), out_cap,
                               _p(_f32c(weight_packed)), _p(scale), _p(shift), _p(residual), int(relu), _p(out), cout,
                               mode, _stream()), 'spconv_fwd')
     _count(1)

@@ -102,8 +102,9 @@ int dz_rulebook_conv(const int32_t* in_coords, const int* d_n_in, int in_cap, in
 /* out[o,:] = act( (sum_k in[nbr[k][o],:] @ W[k]) * scale + shift (+ residual[o,:]) )
  * Replaces SubMConv3d/SparseConv3d forward + BatchNorm1d(eval) + bias + residual add + ReLU
  * (backbone3d.py:64-83,105-121).  weight packed (K, cin, cout) f32 (host side repacks spconv's
- * (cout,KD,KH,KW,cin) layout).  mode: DZ_F32 exact-fp32 FMA, DZ_TF32 / DZ_BF16 tensor cores. */
-int dz_spconv_fwd(const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
+ * (cout,KD,KH,KW,cin) layout; DZ_TF32 expects (cout, K*cin_pad)).  in_rows = allocated rows of `in`
+ * (bounds the TMA gather).  mode: DZ_F32 exact-fp32 FMA, DZ_TF32 tcgen05 tensor cores. */
+int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
                   int out_cap, const float* weight, const float* scale, const float* shift,
                   const float* residual, int relu, float* out, int cout, int mode, dz_stream_t stream);
 

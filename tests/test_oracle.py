@@ -204,3 +204,21 @@ def test_data_processor_and_collate():
     assert (batch['points'][:batch['points_per_frame'][0], 0] == 0).all() and (batch['points'][batch['points_per_frame'][0]:, 0] == 1).all()
     p = np.array([[75.2, 0, 0], [75.3, 0, 0], [0, -75.2, 9]], np.float32)
     assert mask_points_by_range(p, util.WAYMO_RANGE).tolist() == [True, False, True]    # inclusive bound, z unfiltered
+
+
+def test_rotated_iou_restatement_matches_compiled_reference():
+    """oracle/_ref = the reference's own iou3d_cpu.cpp compiled in place (oracle/build_ref.py): the C restatement of
+    the rotated-BEV IoU agrees with it bit for bit"""
+    from oracle import build_ref
+    if not os.path.exists(build_ref.SO):
+        if not os.path.exists(build_ref.REF_SRC):
+            pytest.skip('oracle/_ref not built and /root/reference not mounted')
+        build_ref.build()
+    m = build_ref.load()
+    g = np.random.default_rng(7)
+    n = 300
+    b = np.concatenate([g.uniform(-10, 10, (n, 3)), g.uniform(1, 5, (n, 3)), g.uniform(-3.2, 3.2, (n, 1))], 1).astype(np.float32)
+    b[100:200, :2] = b[:100, :2] + g.normal(0, 0.2, (100, 2)).astype(np.float32)
+    out = torch.zeros(n, n)
+    m.boxes_iou_bev_cpu(torch.from_numpy(b), torch.from_numpy(b), out)
+    assert np.array_equal(out.numpy(), oracle.boxes_iou_bev(b, b))
