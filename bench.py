@@ -42,9 +42,11 @@ def parse():
     ap.add_argument('--backbone', default='VoxelBackBone8x', choices=['VoxelBackBone8x', 'VoxelResBackBone8x'])
     ap.add_argument('--mode', default=os.environ.get('DZ_MODE', 'tf32'),
                     help='dense BEV/head convs: tf32 (tcgen05; what the reference gets from cuDNN by default, SURVEY A.6) | fp32 (exact FMA)')
-    ap.add_argument('--sp-mode', default=os.environ.get('DZ_SP_MODE', 'fp32'), help='sparse-conv arithmetic')
+    ap.add_argument('--sp-mode', default=os.environ.get('DZ_SP_MODE', 'tf32'),
+                    help='sparse-conv arithmetic: tf32 (tcgen05, 1 pass) | tf32x3 (tcgen05, hi/lo split) | fp32 (exact FMA, spconv default)')
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--stage-times', action='store_true', help='print a per-stage device time table to stderr')
     return ap.parse_args()
 
@@ -63,7 +65,13 @@ def build_inputs(batch):
                                n_points=N_POINTS)
     batches = []
     for i in range(NUM_CLOUDS):
-        batches.append(ds.collate_batch([ds[i * batch + j] for j in range(batch)]))
+        items = [ds[i * batch + j] for j in range(batch)]
+        for it in items:                    # fixed shape for CUDA-graph replay: pad with far out-of-range points (dropped by
+            p = it['points']                # the voxelizer exactly like any other out-of-range point)
+            if p.shape[0] < N_POINTS:
+                pad = np.full((N_POINTS - p.shape[0], p.shape[1]), 1.0e4, dtype=np.float32)
+                it['points'] = np.concatenate([p, pad], axis=0)
+        batches.append(ds.collate_batch(items))
     return ds, batches
 
 
@@ -184,15 +192,26 @@ def main():
         b = batches[i % NUM_CLOUDS]
         return {'points': pts, 'points_per_frame': b['points_per_frame'], 'frame_id': b['frame_id'], 'batch_size': b['batch_size']}
 
+    graph_state = {}
+
     def step_resident(i):
+        if graph_state:
+            graph_state['in'].copy_(dev_pts[i % NUM_CLOUDS], non_blocking=True)      # device->device, part of the step
+            graph_state['g'].replay()
+            return graph_state['out']
         with torch.no_grad():
             bd = model.forward_device(batch_dict(i, dev_pts[i % NUM_CLOUDS]))
         return bd
 
     def step_e2e(i):
         with torch.no_grad():
-            pts = host_pts[i % NUM_CLOUDS].to(dev, non_blocking=True)
-            pred, _ = model(batch_dict(i, pts))                       # public API: includes the D2H read of counts
+            if graph_state:
+                graph_state['in'].copy_(host_pts[i % NUM_CLOUDS], non_blocking=True)     # pinned host -> device
+                graph_state['g'].replay()
+                pred, _ = model.post_processing(graph_state['out'])                      # the step's D2H (counts) + dicts
+            else:
+                pts = host_pts[i % NUM_CLOUDS].to(dev, non_blocking=True)
+                pred, _ = model(batch_dict(i, pts))                   # public API: includes the D2H read of counts
             n = pred[0]['pred_boxes'].shape[0]
             out_host[0, :n, :7].copy_(pred[0]['pred_boxes'], non_blocking=True)
         return pred
@@ -214,7 +233,7 @@ def main():
             e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
-        launches = ops.launch_count()
+        launches = ops.launch_count() if not graph_state else graph_state.get('launches_per_step', 0) * steps
         if world > 1:
             dist.barrier()
         total_ms = sum(s.elapsed_time(e) for s, e in evs)
@@ -229,6 +248,16 @@ def main():
             step_e2e(i)
     torch.cuda.synchronize()
 
+    if not args.no_graph:
+        static_pts = dev_pts[0].clone()
+        ops.reset_launch_count()
+        g, out = model.capture_graph(batch_dict(0, static_pts), warmup=0)
+        graph_state.update(g=g, out=out, launches_per_step=ops.launch_count())
+        graph_state['in'] = static_pts
+        for i in range(NUM_CLOUDS):                         # replay sanity: same detections as the eager path
+            step_resident(i)
+        torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     sampler.start()
     total_ms, launches = timed(step_resident, args.steps, args.warmup)
@@ -241,7 +270,10 @@ def main():
     e2e = frames / (e2e_ms / 1000.0)
 
     # ---- roofline of the dominant kernel family: the sparse convolution layers, timed live with CUDA events
-    roof = sparse_conv_roofline(model, step_resident, args, dev)
+    def step_eager(i):
+        with torch.no_grad():
+            return model.forward_device(batch_dict(i, dev_pts[i % NUM_CLOUDS]))
+    roof = sparse_conv_roofline(model, step_eager, args, dev)
 
     line = {
         'metric': 'Waymo-shape frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
@@ -251,7 +283,8 @@ def main():
         'config': {'workload': 'CenterPoint 1-sweep %s, synthetic 180K-pt Waymo-range cloud, fp32, batch %d/GPU'
                                % (args.backbone, args.batch),
                    'sparse_conv_mode': args.sp_mode, 'dense_conv_mode': args.mode, 'parallelism': 'frames sharded dp%d' % world,
-                   'l2': 'flushed (256 MiB write) between steps, outside the timed intervals'},
+                   'l2': 'flushed (256 MiB write) between steps, outside the timed intervals',
+                   'launch': 'eager' if args.no_graph else 'CUDA graph replay of CenterPoint.forward_device'},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(host_pts[0].numel() * 4),
                 'd2h_bytes_per_step': int(args.batch * 4 + 500 * 7 * 4)},
         'gpu_launches': launches,

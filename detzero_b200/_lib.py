@@ -7,8 +7,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdetzero_b200.so')
 
-DZ_F32, DZ_TF32, DZ_BF16 = 0, 1, 2
-MODES = {'fp32': DZ_F32, 'f32': DZ_F32, 'tf32': DZ_TF32, 'bf16': DZ_BF16}
+DZ_F32, DZ_TF32, DZ_BF16, DZ_TF32X3 = 0, 1, 2, 3
+MODES = {'fp32': DZ_F32, 'f32': DZ_F32, 'tf32': DZ_TF32, 'bf16': DZ_BF16, 'tf32x3': DZ_TF32X3, 'fp32_tc': DZ_TF32X3}
 
 _lib = None
 

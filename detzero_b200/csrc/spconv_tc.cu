@@ -124,9 +124,7 @@ k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__
     if (warp < Cfg::STAGES) {
         // ================= producers: warp w fills stage w for the steps w, w+STAGES, ... =================
         const int j = lane & 7;                     // 16-byte chunk inside the 128-byte row
-        const int rg = lane >> 3;                   // rows rg + 4*i, i = 0..31
-        const uint32_t d_even = (uint32_t)(rg * 128 + ((j ^ rg) << 4));
-        const uint32_t d_odd = (uint32_t)((rg + 4) * 128 + ((j ^ (rg + 4)) << 4));
+        const int rg = lane >> 3;                   // lane covers chunk j of rows rg*32 .. rg*32+31
         const int s = warp;
         unsigned char* sa = smem + s * Cfg::STAGE_BYTES;
         const uint32_t sa_u = tc::smem_u32(sa);
@@ -141,21 +139,27 @@ k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__
             const int kidx = kb * 32 + j * 4;       // position in the concatenated (offset, channel) dimension
             const int k = kidx / CIN_PAD, c = kidx % CIN_PAD;
             const bool k_ok = k < K;
-            const int* nb_k = s_nbr + (k_ok ? k : 0) * ST_ROWS + rg;
+            const int4* nb_k = reinterpret_cast<const int4*>(s_nbr + (k_ok ? k : 0) * ST_ROWS + rg * 32);
             const float* in_c = in + c;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const int src_row = k_ok ? nb_k[4 * i] : -1;
-                const uint32_t dst = sa_u + (uint32_t)((i >> 1) * 1024) + ((i & 1) ? d_odd : d_even);
-                if (CIN_PAD >= 16) {
-                    const bool ok = src_row >= 0;
-                    cp_async16_zfill(dst, ok ? (const void*)(in_c + (size_t)src_row * cin) : (const void*)in, ok);
-                } else {
-                    // first layer (cin = 5 padded to 8): rows are not 16-byte aligned -> 4-byte copies
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const bool ok = src_row >= 0 && (c + e) < cin;
-                        cp_async4_zfill(dst + 4 * e, ok ? (const void*)(in_c + (size_t)src_row * cin + e) : (const void*)in, ok);
+            for (int i0 = 0; i0 < 32; i0 += 4) {
+                const int4 nq = nb_k[i0 / 4];
+                const int rows4[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int src_row = k_ok ? rows4[u] : -1;
+                    const int rr = (i0 + u) & 7;    // row r = rg*32 + i0 + u: group rg*4 + (i0+u)/8, row-in-group rr
+                    const uint32_t dst = sa_u + (uint32_t)((rg * 4 + ((i0 + u) >> 3)) * 1024 + rr * 128 + ((j ^ rr) << 4));
+                    if (CIN_PAD >= 16) {
+                        const bool ok = src_row >= 0;
+                        cp_async16_zfill(dst, ok ? (const void*)(in_c + (size_t)src_row * cin) : (const void*)in, ok);
+                    } else {
+                        // first layer (cin = 5 padded to 8): rows are not 16-byte aligned -> 4-byte copies
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const bool ok = src_row >= 0 && (c + e) < cin;
+                            cp_async4_zfill(dst + 4 * e, ok ? (const void*)(in_c + (size_t)src_row * cin + e) : (const void*)in, ok);
+                        }
                     }
                 }
             }
@@ -256,9 +260,14 @@ int dz_spconv_fwd_tc_tma(const float* in, int cin, int in_rows, const int32_t* n
                          const float* weight, const float* scale, const float* shift, const float* residual, int relu, float* out,
                          int cout, cudaStream_t st);
 
+int dz_spconv_fwd_tc3(const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out, int out_cap,
+                      const float* weight, const float* scale, const float* shift, const float* residual, int relu, float* out,
+                      int cout, cudaStream_t st);
+
 int dz_spconv_fwd_tc(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out, int out_cap,
                      const float* weight, const float* scale, const float* shift, const float* residual, int relu, float* out,
                      int cout, int mode, cudaStream_t st) {
+    if (mode == DZ_TF32X3) return dz_spconv_fwd_tc3(in, cin, nbr, K, nbr_cap, d_n_out, out_cap, weight, scale, shift, residual, relu, out, cout, st);
     static int use_tma = getenv("DZ_SPCONV_TMA_GATHER") ? 1 : 0;   // TMA gather4 is slower than the LSU gather for 128-byte rows (profiles/)
     if (mode == DZ_TF32 && use_tma && cin >= 16 && in_rows > 0) {
         int rc = dz_spconv_fwd_tc_tma(in, cin, in_rows, nbr, K, nbr_cap, d_n_out, out_cap, weight, scale, shift, residual, relu, out, cout, st);

@@ -77,6 +77,24 @@ class CenterPoint(nn.Module):
             batch_dict = m(batch_dict)
         return batch_dict
 
+    def capture_graph(self, batch_dict, warmup=2):
+        """Capture forward_device for a fixed input shape in a CUDA graph (streams + graphs instead of a tracing compiler).
+        ``batch_dict['points']`` becomes the static input buffer: copy new points into it, then ``replay()``.  Capacities
+        must have settled (run a few frames through ``forward`` first: the capacity hints are read back there).
+        Returns (graph, static_batch_dict_out)."""
+        import torch
+        static_in = dict(batch_dict)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):
+                self.forward_device(dict(static_in))
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g):
+            out = self.forward_device(dict(static_in))
+        return g, out
+
     def forward(self, batch_dict):
         if self.training:
             raise NotImplementedError('training loop support is a next row (SURVEY.md §8f rank 1)')

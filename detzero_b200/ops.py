@@ -178,7 +178,11 @@ def pack_spconv_weight(w, mode):
     cin_pad = 8 if cin <= 8 else cin
     if cin_pad != cin:
         w = torch.nn.functional.pad(w, (0, cin_pad - cin))
-    return round_tf32(w.reshape(cout, -1).contiguous())
+    w = w.reshape(cout, -1).contiguous()
+    if mode == _lib.DZ_TF32X3:                        # (2, Cout, K*cin_pad): hi = RN_tf32(W), lo = RN_tf32(W - hi)
+        hi = round_tf32(w)
+        return torch.stack([hi, round_tf32(w - hi)]).contiguous()
+    return round_tf32(w)
 
 
 def round_tf32(t):

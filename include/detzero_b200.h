@@ -28,7 +28,8 @@ extern "C" {
 typedef void* dz_stream_t;           /* cudaStream_t */
 
 enum { DZ_OK = 0, DZ_ERR_ARG = -1, DZ_ERR_CUDA = -2, DZ_ERR_WORKSPACE = -3, DZ_ERR_UNSUPPORTED = -4 };
-enum { DZ_F32 = 0, DZ_TF32 = 1, DZ_BF16 = 2 };   /* arithmetic mode of GEMM-shaped kernels */
+enum { DZ_F32 = 0, DZ_TF32 = 1, DZ_BF16 = 2, DZ_TF32X3 = 3 };   /* arithmetic mode of GEMM-shaped kernels:
+   F32 = fp32 FMA; TF32 = one tcgen05 TF32 pass; TF32X3 = hi/lo split, 3 TF32 passes, fp32-level accuracy (sparse conv) */
 
 int         dz_version(void);
 int         dz_sm_arch(void);                      /* 100 : built for sm_100a */

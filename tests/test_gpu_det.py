@@ -134,7 +134,7 @@ def test_spconv_fwd_fp32(cuda, cin, cout):
     ref = torch.relu(ref * scale + shift + res)
     t = SparseConvTensor(f.to(cuda), torch.from_numpy(idx).to(cuda), shape, B)
     nbr = ops.rulebook_subm(t._idx, t._count, t._cap, t.grid_index(), [3, 3, 3])
-    for mode, tol in ((_lib.DZ_F32, 1e-5), (_lib.DZ_TF32, 2e-3)):
+    for mode, tol in ((_lib.DZ_F32, 1e-5), (_lib.DZ_TF32, 2e-3), (_lib.DZ_TF32X3, 2e-5)):     # x3: bounded by the tensor core's fp32 accumulate
         wp = ops.pack_spconv_weight(w, mode).to(cuda)
         out = ops.spconv_fwd(t._feat, nbr, t._count, n, wp, scale.to(cuda), shift.to(cuda), res.to(cuda), True, mode,
                              kshape=(27, cin, cout))
@@ -142,7 +142,8 @@ def test_spconv_fwd_fp32(cuda, cin, cout):
 
 
 @pytest.mark.parametrize('kind,mode,tol', [('VoxelBackBone8x', 'fp32', 2e-5), ('VoxelResBackBone8x', 'fp32', 2e-5),
-                                           ('VoxelBackBone8x', 'tf32', 5e-3), ('VoxelResBackBone8x', 'tf32', 5e-3)])
+                                           ('VoxelBackBone8x', 'tf32', 5e-3), ('VoxelResBackBone8x', 'tf32', 5e-3),
+                                           ('VoxelBackBone8x', 'tf32x3', 1e-4), ('VoxelResBackBone8x', 'tf32x3', 1e-4)])
 def test_backbone3d_vs_oracle(cuda, kind, mode, tol):
     from detzero_b200.det import cp_modules
     cfg = util.model_cfg(kind).BACKBONE_3D
