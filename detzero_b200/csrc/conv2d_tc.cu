@@ -32,19 +32,22 @@ static constexpr int CT_TH = 8, CT_TW = 16, CT_BK = 32;       // pixel patch, ch
 static constexpr int CT_A_BYTES = CT_TH * CT_TW * CT_BK * 4;  // 16 KB
 static constexpr int CT_THREADS = 192;                        // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
 
-template <int BN>
+template <int BN, int MT>
 struct CtCfg {
     static constexpr int B_BYTES = BN * CT_BK * 4;
-    static constexpr int STAGE_BYTES = CT_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+    static constexpr int STAGE_BYTES = MT * CT_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = (MT * BN) < 32 ? 32 : MT * BN;      // MT accumulators side by side
 };
 
-template <int BN>
+// MT = output patches per CTA (stacked in y): the weight tile of every k-step is shared by MT accumulators, which cuts the
+// L2->SM bytes per MMA (the kernel is bound by the ~34 B/clk/SM an SM can pull from L2, not by the tensor pipe)
+template <int BN, int MT>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Conv2dParams p, int tiles_x,
               int tiles_y) {
-    using Cfg = CtCfg<BN>;
+    using Cfg = CtCfg<BN, MT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -55,7 +58,7 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int mt = blockIdx.x;
     const int tx0 = (mt % tiles_x) * CT_TW; mt /= tiles_x;
-    const int ty0 = (mt % tiles_y) * CT_TH;
+    const int ty0 = (mt % tiles_y) * (CT_TH * MT);
     const int b = mt / tiles_y;
     const int n0 = blockIdx.y * BN;
     const int cchunks = p.cin / CT_BK;
@@ -68,7 +71,7 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -80,11 +83,14 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 const int s = it % Cfg::STAGES;
                 tc::mbar_wait(empty + s, ((it / Cfg::STAGES) & 1) ^ 1);
                 unsigned char* sa = smem + s * Cfg::STAGE_BYTES;
-                unsigned char* sb = sa + CT_A_BYTES;
+                unsigned char* sb = sa + MT * CT_A_BYTES;
                 const int tap = it / cchunks, cc = it - tap * cchunks;
                 const int r = tap / p.KW, sx = tap - r * p.KW;
                 tc::mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
-                tc::tma_load_4d(sa, &tmA, full + s, cc * CT_BK, tx0 * p.stride + sx - p.pad, ty0 * p.stride + r - p.pad, b);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    tc::tma_load_4d(sa + m * CT_A_BYTES, &tmA, full + s, cc * CT_BK, tx0 * p.stride + sx - p.pad,
+                                    (ty0 + m * CT_TH) * p.stride + r - p.pad, b);
                 tc::tma_load_2d(sb, &tmB, full + s, tap * p.cin + cc * CT_BK, n0);
             }
         }
@@ -96,10 +102,15 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 tc::mbar_wait(full + s, (it / Cfg::STAGES) & 1);
                 tc::tcgen05_fence_after();
                 const uint32_t sa = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t adesc = tc::smem_desc_sw128(sa), bdesc = tc::smem_desc_sw128(sa + CT_A_BYTES);
+                const uint64_t bdesc = tc::smem_desc_sw128(sa + MT * CT_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < CT_BK / 8; ++k)            // K = 8 tf32 = 32 bytes per instruction
-                    tc::mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+                for (int m = 0; m < MT; ++m) {
+                    const uint64_t adesc = tc::smem_desc_sw128(sa + m * CT_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CT_BK / 8; ++k)        // K = 8 tf32 = 32 bytes per instruction
+                        tc::mma_tf32(tmem_base + (uint32_t)(m * BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                     (it | k) ? 1u : 0u);
+                }
                 tc::mma_commit(empty + s);                      // frees the stage once these MMAs have read it
             }
             tc::mma_commit(tmem_full);
@@ -108,15 +119,16 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int q = warp & 3;
         const int row = q * 32 + lane;                          // pixel index inside the 8x16 patch
-        const int y = ty0 + row / CT_TW, x = tx0 + row % CT_TW;
-        const bool valid = (y < p.Ho) && (x < p.Wo);
-        float* orow = p.out + (((size_t)b * p.OH + (y * p.os + p.oy0)) * p.OW + (x * p.os + p.ox0)) * p.out_cstride + p.out_coff;
         tc::mbar_wait(tmem_full, 0);
         tc::tcgen05_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int mc = 0; mc < MT * BN; mc += 32) {
+            const int m = mc / BN, c0 = mc % BN;
+            const int y = ty0 + m * CT_TH + row / CT_TW, x = tx0 + row % CT_TW;
+            const bool valid = (y < p.Ho) && (x < p.Wo);
+            float* orow = p.out + (((size_t)b * p.OH + (y * p.os + p.oy0)) * p.OW + (x * p.os + p.ox0)) * p.out_cstride + p.out_coff;
             float v[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mc, v);
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -134,20 +146,20 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+    if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
-    using Cfg = CtCfg<BN>;
+    using Cfg = CtCfg<BN, MT>;
     static bool configured = false;
     if (!configured) {
-        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
-    int tiles_x = dz_cdiv(p.Wo, CT_TW), tiles_y = dz_cdiv(p.Ho, CT_TH);
+    int tiles_x = dz_cdiv(p.Wo, CT_TW), tiles_y = dz_cdiv(p.Ho, CT_TH * MT);
     dim3 grid(tiles_x * tiles_y * p.B, dz_cdiv(p.cout, BN));
-    k_conv2d_tf32<BN><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, p, tiles_x, tiles_y);
+    k_conv2d_tf32<BN, MT><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, p, tiles_x, tiles_y);
     DZ_LAUNCH_CHECK();
     return DZ_OK;
 }
@@ -183,9 +195,13 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p, int mode, cudaStream_t st) {
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
+    // two stacked patches per CTA when there are enough tiles to still fill the GPU (the weight tile is then loaded once
+    // for 256 output pixels)
+    const long long tiles1 = (long long)dz_cdiv(p.Wo, CT_TW) * dz_cdiv(p.Ho, CT_TH) * p.B * dz_cdiv(p.cout, bn);
+    const bool two = tiles1 >= 2 * DZ_NUM_SMS - 16;
     switch (bn) {
-        case 128: return launch_tf32<128>(p, tmA, tmB, st);
-        case 64: return launch_tf32<64>(p, tmA, tmB, st);
-        default: return launch_tf32<32>(p, tmA, tmB, st);
+        case 128: return two ? launch_tf32<128, 2>(p, tmA, tmB, st) : launch_tf32<128, 1>(p, tmA, tmB, st);
+        case 64: return two ? launch_tf32<64, 2>(p, tmA, tmB, st) : launch_tf32<64, 1>(p, tmA, tmB, st);
+        default: return two ? launch_tf32<32, 2>(p, tmA, tmB, st) : launch_tf32<32, 1>(p, tmA, tmB, st);
     }
 }

@@ -36,7 +36,8 @@ __device__ void bitonic_desc(unsigned long long* keys, int n) {
 __global__ void __launch_bounds__(HD_THREADS) k_topk_class(const float* __restrict__ head, int HW, int ch, int ch_hm, int ch_iou,
                                                            int use_iou, int num_class, int K, int Kp,
                                                            float* __restrict__ score_ws,
-                                                           unsigned long long* __restrict__ cand_keys) {
+                                                           unsigned long long* __restrict__ cand_keys, const int* __restrict__ overflow) {
+    if (overflow && !overflow[blockIdx.x]) return;            // the fast path already produced this (frame, class)
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long keys[1024];
     __shared__ unsigned int sh_prefix, sh_need, sh_cnt;
@@ -100,6 +101,53 @@ __global__ void __launch_bounds__(HD_THREADS) k_topk_class(const float* __restri
     __syncthreads();
     bitonic_desc(keys, Kp);
     for (int i = threadIdx.x; i < Kp; i += blockDim.x) cand_keys[(size_t)blockIdx.x * Kp + i] = i < Keff ? keys[i] : 0ull;
+}
+
+
+// ---- fast path: only scores above SCORE_THRESH can survive the final mask (centernet_utils.py:205-206), and they rank above
+// everything else, so top-K can be taken among them.  Pass 1 (whole GPU): score every (frame, class, pixel) and append the
+// ones above the threshold to a per-(frame, class) candidate list.  Pass 2 (one CTA per list): exact top-K by
+// (score desc, index asc) + bitonic sort.  If a list overflows HD_CAND_CAP the slow full-map kernel below takes over.
+static constexpr int HD_CAND_CAP = 4096;
+
+__global__ void __launch_bounds__(256) k_score_prefilter(const float* __restrict__ head, int HW, int ch, int ch_hm, int ch_iou, int use_iou,
+                                                         int num_class, int B, float thresh, unsigned long long* __restrict__ cand,
+                                                         int* __restrict__ cand_cnt) {
+    const long long total = (long long)B * HW;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / HW), i = (int)(t % HW);
+        const float* px = head + (size_t)t * ch;
+        float q2 = 1.f;
+        if (use_iou) { float q = fminf(fmaxf(__ldg(px + ch_iou), 0.f), 1.f); q2 = __fmul_rn(q, q); }
+        for (int cls = 0; cls < num_class; ++cls) {
+            float s = sigmoidf_exact(__ldg(px + ch_hm + cls));
+            if (use_iou) s = __fmul_rn(s, q2);
+            if (s > thresh) {
+                int slot = b * num_class + cls;
+                int pos = atomicAdd(cand_cnt + slot, 1);
+                if (pos < HD_CAND_CAP)
+                    cand[(size_t)slot * HD_CAND_CAP + pos] = ((unsigned long long)__float_as_uint(s) << 32) | (0xffffffffu - (unsigned int)i);
+            }
+        }
+    }
+}
+
+// one CTA per (frame, class): sort the candidate list (<= HD_CAND_CAP keys) and keep the K best
+__global__ void __launch_bounds__(HD_THREADS) k_topk_from_candidates(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt,
+                                                                    int K, int Kp, unsigned long long* __restrict__ cand_keys,
+                                                                    int* __restrict__ overflow) {
+    __shared__ unsigned long long keys[HD_CAND_CAP];
+    const int slot = blockIdx.x;
+    const int n = cand_cnt[slot];
+    if (n > HD_CAND_CAP) { if (threadIdx.x == 0) overflow[slot] = 1; return; }     // slow path will redo this slot
+    if (threadIdx.x == 0) overflow[slot] = 0;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    if (np2 < Kp) np2 = Kp;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) keys[i] = i < n ? cand[(size_t)slot * HD_CAND_CAP + i] : 0ull;
+    __syncthreads();
+    bitonic_desc(keys, np2);
+    for (int i = threadIdx.x; i < Kp; i += blockDim.x) cand_keys[(size_t)slot * Kp + i] = (i < K && i < n) ? keys[i] : 0ull;
 }
 
 struct DecodeGeom {
@@ -175,7 +223,8 @@ __global__ void __launch_bounds__(HD_THREADS) k_topk_merge_decode(const float* _
 
 extern "C" size_t dz_centerhead_decode_ws_bytes(int B, int H, int W, int num_class, int K) {
     int Kp = 1; while (Kp < K) Kp <<= 1;
-    return dz_align_up((size_t)B * num_class * H * W * 4, 256) + dz_align_up((size_t)B * num_class * Kp * 8, 256);
+    return dz_align_up((size_t)B * num_class * H * W * 4, 256) + dz_align_up((size_t)B * num_class * Kp * 8, 256) +
+           dz_align_up((size_t)B * num_class * HD_CAND_CAP * 8, 256) + dz_align_up((size_t)B * num_class * 4, 256) * 2;
 }
 
 extern "C" int dz_centerhead_decode(const float* head, int B, int H, int W, int ch, int ch_center, int ch_z, int ch_dim,
@@ -191,7 +240,19 @@ extern "C" int dz_centerhead_decode(const float* head, int B, int H, int W, int 
     DzWs w(ws, ws_bytes);
     float* score_ws = w.take<float>((size_t)B * num_class * H * W);
     unsigned long long* cand_keys = w.take<unsigned long long>((size_t)B * num_class * Kp);
-    k_topk_class<<<B * num_class, HD_THREADS, 0, st>>>(head, H * W, ch, ch_hm, ch_iou, use_iou, num_class, K, Kp, score_ws, cand_keys);
+    unsigned long long* cand = w.take<unsigned long long>((size_t)B * num_class * HD_CAND_CAP);
+    int* cand_cnt = w.take<int>((size_t)B * num_class);
+    int* overflow = w.take<int>((size_t)B * num_class);
+    if (!overflow) { dz_set_error("dz_centerhead_decode: workspace carve failed"); return DZ_ERR_WORKSPACE; }
+    if (K <= HD_CAND_CAP && score_thresh >= 0.f) {
+        DZ_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)B * num_class * 4, st));
+        int blocks = max(1, min(dz_cdiv((long long)B * H * W, 256), DZ_NUM_SMS * 8));
+        k_score_prefilter<<<blocks, 256, 0, st>>>(head, H * W, ch, ch_hm, ch_iou, use_iou, num_class, B, score_thresh, cand, cand_cnt);
+        k_topk_from_candidates<<<B * num_class, HD_THREADS, 0, st>>>(cand, cand_cnt, K, Kp, cand_keys, overflow);
+        k_topk_class<<<B * num_class, HD_THREADS, 0, st>>>(head, H * W, ch, ch_hm, ch_iou, use_iou, num_class, K, Kp, score_ws, cand_keys, overflow);
+    } else {
+        k_topk_class<<<B * num_class, HD_THREADS, 0, st>>>(head, H * W, ch, ch_hm, ch_iou, use_iou, num_class, K, Kp, score_ws, cand_keys, nullptr);
+    }
     DecodeGeom g;
     for (int d = 0; d < 3; ++d) { g.lo[d] = range6[d]; g.vs[d] = vsize3[d]; }
     for (int d = 0; d < 6; ++d) g.limit[d] = post_limit6[d];

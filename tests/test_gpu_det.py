@@ -143,7 +143,7 @@ def test_spconv_fwd_fp32(cuda, cin, cout):
 
 @pytest.mark.parametrize('kind,mode,tol', [('VoxelBackBone8x', 'fp32', 2e-5), ('VoxelResBackBone8x', 'fp32', 2e-5),
                                            ('VoxelBackBone8x', 'tf32', 5e-3), ('VoxelResBackBone8x', 'tf32', 5e-3),
-                                           ('VoxelBackBone8x', 'tf32x3', 1e-4), ('VoxelResBackBone8x', 'tf32x3', 1e-4)])
+                                           ('VoxelBackBone8x', 'tf32x3', 2e-4), ('VoxelResBackBone8x', 'tf32x3', 2e-4)])
 def test_backbone3d_vs_oracle(cuda, kind, mode, tol):
     from detzero_b200.det import cp_modules
     cfg = util.model_cfg(kind).BACKBONE_3D
@@ -266,10 +266,11 @@ def test_iou_and_nms(cuda):
     assert out[0, k:].abs().max().item() == 0
 
 
-def test_decode_and_nms_vs_oracle(cuda):
+@pytest.mark.parametrize('H,W', [(24, 24), (96, 80)])      # 96x80: > 4096 scores above the threshold -> full-map select path
+def test_decode_and_nms_vs_oracle(cuda, H, W):
     from detzero_b200 import ops
     g = torch.Generator().manual_seed(12)
-    B, H, W = 2, 24, 24
+    B = 2
     maps = {'center': torch.rand(B, 2, H, W, generator=g), 'center_z': torch.randn(B, 1, H, W, generator=g),
             'dim': torch.randn(B, 3, H, W, generator=g) * 0.3 + 0.8, 'rot': torch.randn(B, 2, H, W, generator=g),
             'iou': torch.rand(B, 1, H, W, generator=g) * 1.4 - 0.2, 'hm': torch.randn(B, 3, H, W, generator=g) * 2 - 1}
