@@ -205,3 +205,24 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p, int mode, cudaStream_t st) {
         default: return two ? launch_tf32<32, 2>(p, tmA, tmB, st) : launch_tf32<32, 1>(p, tmA, tmB, st);
     }
 }
+
+
+// y = act((x @ W^T) * scale + shift) on the tensor cores: a linear layer is a 1x1 convolution over an "image" of width 16
+// whose pixels are the rows of x (an 8 x 16 patch == 128 consecutive rows), so the implicit-GEMM kernel above serves
+// F.linear / Conv1d(k=1) / Conv2d(k=1) of the refiner (utils/detzero_utils/model_utils.py:81-134) unchanged.
+// Requirements: K % 32 == 0, N % 4 == 0, ldy % 4 == 0; the M % 16 tail rows go through the exact-fp32 kernel.
+int dz_linear_fwd_f32_rows(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
+                           float* y, int ldy, cudaStream_t st);
+
+int dz_linear_fwd_tc(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu, float* y,
+                     int ldy, int mode, cudaStream_t st) {
+    if (mode != DZ_TF32) { dz_set_error("dz_linear_fwd: tensor-core mode %d not built (tf32 only)", mode); return DZ_ERR_UNSUPPORTED; }
+    if (K % 32 != 0 || N % 4 != 0 || ldy % 4 != 0 || M < 16)      // shapes the TMA path cannot express: exact-fp32 kernel (more precise)
+        return dz_linear_fwd_f32_rows(x, M, K, w, N, scale, shift, relu, y, ldy, st);
+    const int H = M / 16, tail = M - H * 16;
+    Conv2dParams p{x, w, scale, shift, y, 1, H, 16, K, K, 1, 1, 1, 0, H, 16, N, H, 16, 1, 0, 0, 0, ldy, relu};
+    int rc = dz_conv2d_fwd_tc(p, DZ_TF32, st);
+    if (rc) return rc;
+    if (tail) return dz_linear_fwd_f32_rows(x + (size_t)H * 16 * K, tail, K, w, N, scale, shift, relu, y + (size_t)H * 16 * ldy, ldy, st);
+    return DZ_OK;
+}

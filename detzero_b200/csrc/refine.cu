@@ -90,6 +90,15 @@ __global__ void __launch_bounds__(LN_THREADS) k_linear_f32(const float* __restri
 int dz_linear_fwd_tc(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
                      float* y, int ldy, int mode, cudaStream_t st);
 
+int dz_linear_fwd_f32_rows(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
+                           float* y, int ldy, cudaStream_t st) {
+    if (M <= 0) return DZ_OK;
+    dim3 grid(dz_cdiv(M, LN_BM), dz_cdiv(N, LN_BN));
+    k_linear_f32<<<grid, LN_THREADS, 0, st>>>(x, M, K, w, N, scale, shift, relu, y, ldy);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
+}
+
 extern "C" int dz_linear_fwd(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift,
                              int relu, float* y, int ldy, int mode, dz_stream_t stream) {
     DZ_CHECK_ARG(x && w && y && M >= 0 && K >= 1 && N >= 1 && ldy >= N);

@@ -2,9 +2,6 @@
 // fallback to the fp32 path.
 #include "common.cuh"
 
-int dz_linear_fwd_tc(const float*, int, int, const float*, int, const float*, const float*, int, float*, int, int mode, cudaStream_t) {
-    dz_set_error("dz_linear_fwd: tensor-core mode %d not built", mode); return DZ_ERR_UNSUPPORTED;
-}
 int dz_attention_fwd_tc(const float*, int, const float*, int, const float*, int, const unsigned char*, int, int, int, int, int,
                         float*, int, int mode, cudaStream_t) {
     dz_set_error("dz_attention_fwd: tensor-core mode %d not built", mode); return DZ_ERR_UNSUPPORTED;

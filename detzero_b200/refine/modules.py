@@ -54,10 +54,22 @@ def make_conv_layers(cfg, c_in, c_out, output_use_norm=False):
     return nn.Sequential(*layers)
 
 
-def _w2d(m):
-    """weight of Linear / Conv1d(k=1) / Conv2d(k=1) as (N, K)"""
-    w = m.weight.detach()
-    return w.reshape(w.shape[0], -1).contiguous().float()
+_w_cache = {}
+
+
+def _w2d(m, mode=_lib.DZ_F32):
+    """weight of Linear / Conv1d(k=1) / Conv2d(k=1) as (N, K); rounded to TF32 (RN) once for the tensor-core mode"""
+    w = m.weight
+    key = (id(m), mode)
+    ver = (w._version, w.data_ptr())
+    hit = _w_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w2 = w.detach().reshape(w.shape[0], -1).contiguous().float()
+    if mode == _lib.DZ_TF32:
+        w2 = ops.round_tf32(w2)
+    _w_cache[key] = (ver, w2)
+    return w2
 
 
 def run_mlp(seq, x, mode, upto=None, taps=None):
@@ -75,7 +87,7 @@ def run_mlp(seq, x, mode, upto=None, taps=None):
             scale, shift = fold_bn(bn, m.bias)
         else:
             scale, shift = None, (None if m.bias is None else m.bias.detach().float())
-        x = ops.linear(x, _w2d(m), scale, shift, relu, mode=mode)
+        x = ops.linear(x, _w2d(m, mode), scale, shift, relu, mode=mode)
         i = j + (1 if relu else 0)
         if taps is not None and (i - 1) in taps:
             taps[i - 1] = x
@@ -132,7 +144,9 @@ class MultiheadAttention(nn.Module):
             w, s, b = self._scaled(E, 3 * E, False)
             kv = ops.linear(key.reshape(B * Pk, E), w, None, b, False, mode=mode).view(B, Pk, 2 * E)
             k, v = kv[:, :, :E], kv[:, :, E:]
-        att = ops.attention(q, k, v, key_padding_mask, self.num_heads, mode=mode)
+        # the attention core (QK^T, softmax, PV; head_dim 32) runs in exact fp32 in every mode this round: it is exp/softmax-bound,
+        # the tensor-core version is the next kernel
+        att = ops.attention(q, k, v, key_padding_mask, self.num_heads, mode=_lib.DZ_F32)
         out = ops.linear(att.view(B * Pq, E), self.out_proj.weight.detach().float().contiguous(), None,
                          None if self.out_proj.bias is None else self.out_proj.bias.detach().float(), False, mode=mode)
         return out.view(B, Pq, E)
@@ -213,9 +227,9 @@ class FFN(nn.Module):
             for m in getattr(self, head):
                 if isinstance(m, ConvModule):
                     s, b = fold_bn(m.bn, None)
-                    h = ops.linear(h, _w2d(m.conv), s, b, True, mode=mode)
+                    h = ops.linear(h, _w2d(m.conv, mode), s, b, True, mode=mode)
                 else:
-                    h = ops.linear(h, _w2d(m), None, m.bias.detach().float(), False, mode=mode)
+                    h = ops.linear(h, _w2d(m, mode), None, m.bias.detach().float(), False, mode=mode)
             out[head] = h
         return out
 
