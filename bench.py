@@ -323,8 +323,12 @@ def sparse_conv_roofline(model, step_fn, args, dev):
         tot_flops += 2.0 * pairs * cin * cout
         tot_ms += r['start'].elapsed_time(r['end'])
     achieved = tot_bytes / (tot_ms / 1000.0) / 1e9 if tot_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath) and args.sp_mode == 'tf32' and args.backbone == 'VoxelBackBone8x':
+        traffic = json.load(open(tpath))['sparse_conv_dram_bytes_per_frame']      # from the committed ncu --set full capture
     return {'bound': 'hbm', 'kernel': 'k_spconv (all %d sparse-conv launches of one frame)' % len(rec), 'achieved': achieved,
-            'peak': peak, 'peak_source': which, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'peak': peak, 'peak_source': which, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
             'algorithmic_bytes_per_frame': tot_bytes, 'algorithmic_flops_per_frame': tot_flops, 'ms_per_frame': tot_ms}
 
 

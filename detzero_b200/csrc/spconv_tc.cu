@@ -50,9 +50,12 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-template <int CIN_PAD, int COUT>
+// HYB: the last stage is filled by the TMA unit (tile::gather4, one instruction per 4 rows) instead of an LSU (cp.async) warp.
+// The LSU gather is issue-bound and the TMA gather is TMA-bound (profiles/r01_spconv_notes.md); they are different pieces of
+// hardware, so splitting the k-steps between them raises the aggregate gather rate.
+template <int CIN_PAD, int COUT, bool HYB>
 __global__ void __launch_bounds__(StCfg<COUT>::THREADS)
-k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ in, int cin, const int32_t* __restrict__ nbr, int K,
+k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, int in_rows, const float* __restrict__ in, int cin, const int32_t* __restrict__ nbr, int K,
               int nbr_cap, const int* __restrict__ d_n_out, int out_cap, const float* __restrict__ scale,
               const float* __restrict__ shift, const float* __restrict__ residual, int relu, float* __restrict__ out, int dbg, long long* __restrict__ dbgbuf) {
     using Cfg = StCfg<COUT>;
@@ -79,7 +82,8 @@ k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__
 
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmW);
-        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full + s, 32 + 1); tc::mbar_init(empty + s, 1); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full + s, (HYB && s == Cfg::STAGES - 1) ? 1 : 32 + 1); tc::mbar_init(empty + s, 1); }
+        if (HYB) tc::prefetch_tmap(&tmA);
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
         *s_mask = 0u;
@@ -121,7 +125,26 @@ k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__
     const uint32_t tmem_base = *tmem_slot;
     if (tr && threadIdx.x == 0) { dbgbuf[1] = clock64(); dbgbuf[2] = nb; }
 
-    if (warp < Cfg::STAGES) {
+    if (HYB && warp == Cfg::STAGES - 1) {
+        // ================= TMA-gather producer (stage STAGES-1): lane l gathers rows 4l..4l+3 of the 128-row block =========
+        const int s = warp;
+        unsigned char* sa = smem + s * Cfg::STAGE_BYTES;
+        constexpr int BPK = CIN_PAD / 32;            // 32-float blocks per kernel offset (CIN_PAD >= 32 in this mode)
+        for (int it = warp, round = 0; it < nb; it += Cfg::STAGES, ++round) {
+            const int kb = s_blocks[it];
+            const int k = kb / BPK, c0 = (kb % BPK) * 32;
+            tc::mbar_wait(empty + s, (round & 1) ^ 1);
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
+                tc::tma_load_2d(sa + ST_A_BYTES, &tmW, full + s, kb * 32, 0);
+            }
+            __syncwarp();
+            int4 rows = *reinterpret_cast<const int4*>(s_nbr + k * ST_ROWS + lane * 4);
+            rows.x = rows.x < 0 ? in_rows : rows.x; rows.y = rows.y < 0 ? in_rows : rows.y;      // out of range => zero fill
+            rows.z = rows.z < 0 ? in_rows : rows.z; rows.w = rows.w < 0 ? in_rows : rows.w;
+            tc::tma_gather4(sa + lane * 512, &tmA, full + s, c0, rows.x, rows.y, rows.z, rows.w);
+        }
+    } else if (warp < Cfg::STAGES) {
         // ================= producers: warp w fills stage w for the steps w, w+STAGES, ... =================
         const int j = lane & 7;                     // 16-byte chunk inside the 128-byte row
         const int rg = lane >> 3;                   // lane covers chunk j of rows rg*32 .. rg*32+31
@@ -233,23 +256,34 @@ extern "C" int dz_debug_trace(long long* host, int n) {      // DEBUG helper (no
 }
 
 template <int CIN_PAD, int COUT>
-static int launch(const CUtensorMap& tmW, const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
+static int launch(const CUtensorMap& tmW, const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
                   int out_cap, const float* scale, const float* shift, const float* residual, int relu, float* out, cudaStream_t st) {
     using Cfg = StCfg<COUT>;
+    constexpr bool HYB = false;      // hybrid LSU+TMA gather measured: no gain over the LSU-only gather (profiles/r01_spconv_notes.md)
+    CUtensorMap tmA = tmW;
+    if (HYB) {
+        tc::EncodeTiledFn enc = tc::get_encode_tiled();
+        cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)in_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)cin * 4};
+        cuuint32_t box[2] = {32, 1};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(A gather) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
     static bool configured = false;
     if (!configured) {
-        DZ_CUDA(cudaFuncSetAttribute(k_spconv_tf32<CIN_PAD, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DZ_CUDA(cudaFuncSetAttribute(k_spconv_tf32<CIN_PAD, COUT, HYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
     static int dbg = getenv("DZ_SPCONV_DBG") ? atoi(getenv("DZ_SPCONV_DBG")) : 0;
     static int pad = getenv("DZ_SPCONV_SMEM_PAD") ? atoi(getenv("DZ_SPCONV_SMEM_PAD")) : 0;
     static bool configured2 = false;
     if (!configured2) {
-        if (pad) DZ_CUDA(cudaFuncSetAttribute(k_spconv_tf32<CIN_PAD, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM + pad));
-        if (getenv("DZ_SPCONV_CARVEOUT")) DZ_CUDA(cudaFuncSetAttribute(k_spconv_tf32<CIN_PAD, COUT>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("DZ_SPCONV_CARVEOUT"))));
+        if (pad) DZ_CUDA(cudaFuncSetAttribute(k_spconv_tf32<CIN_PAD, COUT, HYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM + pad));
         configured2 = true;
     }
-    k_spconv_tf32<CIN_PAD, COUT><<<dz_cdiv(out_cap, ST_ROWS), Cfg::THREADS, Cfg::SMEM + pad, st>>>(tmW, in, cin, nbr, K, nbr_cap, d_n_out, out_cap,
+    k_spconv_tf32<CIN_PAD, COUT, HYB><<<dz_cdiv(out_cap, ST_ROWS), Cfg::THREADS, Cfg::SMEM + pad, st>>>(tmW, tmA, in_rows, in, cin, nbr, K, nbr_cap, d_n_out, out_cap,
                                                                                           scale, shift, residual, relu, out, dbg, g_dbgbuf);
     DZ_LAUNCH_CHECK();
     return DZ_OK;
@@ -289,7 +323,7 @@ int dz_spconv_fwd_tc(const float* in, int cin, int in_rows, const int32_t* nbr, 
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(W) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
-#define DZ_ST(CP, CO) return launch<CP, CO>(tmW, in, cin, nbr, K, nbr_cap, d_n_out, out_cap, scale, shift, residual, relu, out, st)
+#define DZ_ST(CP, CO) return launch<CP, CO>(tmW, in, cin, in_rows, nbr, K, nbr_cap, d_n_out, out_cap, scale, shift, residual, relu, out, st)
     if (cin_pad == 8 && cout == 16) DZ_ST(8, 16);
     if (cin_pad == 16 && cout == 16) DZ_ST(16, 16);
     if (cin_pad == 16 && cout == 32) DZ_ST(16, 32);

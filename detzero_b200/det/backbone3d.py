@@ -62,15 +62,55 @@ class _Backbone8xBase(nn.Module):
                                        batch_size=batch_dict['batch_size'],
                                        count=batch_dict.get('voxel_count'), index=batch_dict.get('voxel_grid_index'))
 
+    def _first_convs(self):
+        """first conv of every indice_key, in execution order (the rulebook chain depends on coordinates only)"""
+        seen, order = set(), []
+        for m in self.modules():
+            if isinstance(m, spconv._SparseConv) and m.indice_key not in seen:
+                seen.add(m.indice_key)
+                order.append(m)
+        return order
+
+    def prebuild_rulebooks(self, x0):
+        """Build all rulebooks of the frame on a side stream while the feature convolutions run on the main stream:
+        rulebooks depend only on coordinates, so the whole chain (spconv2 -> subm2 -> spconv3 -> ...) can run ahead of the
+        features.  Every conv waits on its own rulebook's event.  Captured as parallel branches by CUDA graphs."""
+        main = torch.cuda.current_stream()
+        if getattr(self, '_side', None) is None or self._side.device != x0._feat.device:
+            self._side = torch.cuda.Stream(device=x0._feat.device)
+        side = self._side
+        side.wait_stream(main)
+        events = {}
+        with torch.cuda.stream(side):
+            t = x0
+            for conv in self._first_convs():
+                rule = conv._rule(t)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events[conv.indice_key] = ev
+                if not conv.subm:                       # coordinates-only view of the strided conv's output sites
+                    t = spconv.SparseConvTensor(t._feat[:1].new_empty((rule.out_cap, 1)), rule.out_idx, rule.out_dhw, t.batch_size,
+                                                indice_dict=t.indice_dict, count=rule.d_n_out, n_host=None, index=rule.out_index)
+                    t._producer = conv
+        x0.indice_dict['__events__'] = events
+        x0.indice_dict['__side__'] = side
+
     def forward(self, batch_dict):
         if self.training:
             raise NotImplementedError('sparse-conv backward / train-mode BN is a next row (SURVEY.md §8f rank 1)')
-        x = self.conv_input(self._input_tensor(batch_dict))
+        x0 = self._input_tensor(batch_dict)
+        if self.model_cfg.get('OVERLAP_RULEBOOKS', True) if hasattr(self.model_cfg, 'get') else True:
+            self.prebuild_rulebooks(x0)
+        x = self.conv_input(x0)
         x_conv1 = self.conv1(x)
         x_conv2 = self.conv2(x_conv1)
         x_conv3 = self.conv3(x_conv2)
         x_conv4 = self.conv4(x_conv3)
         out = self.conv_out(x_conv4)
+        side = x0.indice_dict.pop('__side__', None)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)            # join (all rulebook memory is safe to reuse afterwards)
+            x0.indice_dict.pop('__events__', None)
         batch_dict.update({'encoded_spconv_tensor': out, 'encoded_spconv_tensor_stride': 8})
         batch_dict.update({'multi_scale_3d_features': {'x_conv1': x_conv1, 'x_conv2': x_conv2, 'x_conv3': x_conv3,
                                                        'x_conv4': x_conv4}})

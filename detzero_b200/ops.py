@@ -89,7 +89,7 @@ def grid_index_from_coords(coords, d_n, cap, B, dhw, with_perm=True):
     _need_cuda(coords)
     gi = GridIndex(B, dhw, coords.device, with_perm_cap=cap if with_perm else None)
     total = torch.zeros(1, dtype=torch.int32, device=coords.device)
-    ws = workspace(scan_ws_bytes(gi.words), coords.device)
+    ws = workspace(scan_ws_bytes(gi.words), coords.device, 'rulebook')
     check(lib().dz_grid_index_from_coords(_p(coords), _p(d_n), cap, gi.B, *gi.dhw, _p(gi.bitmap), _p(gi.prefix),
                                           _p(gi.perm), _p(total), _p(ws), ws.numel(), _stream()), 'grid_index_from_coords')
     _count(5)
@@ -159,7 +159,7 @@ def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap):
     out_coords = torch.zeros((out_cap, 4), dtype=torch.int32, device=dev)
     d_n_out = torch.zeros(1, dtype=torch.int32, device=dev)
     nbr = torch.empty((K, out_cap), dtype=torch.int32, device=dev)
-    ws = workspace(scan_ws_bytes(out_index.words), dev)
+    ws = workspace(scan_ws_bytes(out_index.words), dev, 'rulebook')      # own scratch: rulebooks run on a side stream
     check(lib().dz_rulebook_conv(_p(coords), _p(d_n), in_cap, in_index.B, iarr(in_index.dhw), iarr(ksize), iarr(stride),
                                  iarr(pad), _p(in_index.bitmap), _p(in_index.prefix), _p(in_index.perm), _p(out_coords),
                                  _p(d_n_out), out_cap, _p(out_index.bitmap), _p(out_index.prefix), _p(nbr), _p(ws),

@@ -206,6 +206,9 @@ class _SparseConv(SparseModule):
 
     def forward_fused(self, x, scale=None, shift=None, residual=None, relu=False):
         rule = self._rule(x)
+        evs = x.indice_dict.get('__events__')
+        if evs is not None and self.indice_key in evs:               # rulebook was built on the side stream
+            torch.cuda.current_stream().wait_event(evs[self.indice_key])
         mode = _lib.MODES[self.mode]
         if self.subm:
             out = ops.spconv_fwd(x._feat, rule.nbr, x._count, x._cap, self.packed_weight(mode), scale, shift,
