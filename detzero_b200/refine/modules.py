@@ -144,9 +144,7 @@ class MultiheadAttention(nn.Module):
             w, s, b = self._scaled(E, 3 * E, False)
             kv = ops.linear(key.reshape(B * Pk, E), w, None, b, False, mode=mode).view(B, Pk, 2 * E)
             k, v = kv[:, :, :E], kv[:, :, E:]
-        # the attention core (QK^T, softmax, PV; head_dim 32) runs in exact fp32 in every mode this round: it is exp/softmax-bound,
-        # the tensor-core version is the next kernel
-        att = ops.attention(q, k, v, key_padding_mask, self.num_heads, mode=_lib.DZ_F32)
+        att = ops.attention(q, k, v, key_padding_mask, self.num_heads, mode=mode)
         out = ops.linear(att.view(B * Pq, E), self.out_proj.weight.detach().float().contiguous(), None,
                          None if self.out_proj.bias is None else self.out_proj.bias.detach().float(), False, mode=mode)
         return out.view(B, Pq, E)

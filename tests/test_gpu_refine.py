@@ -38,8 +38,9 @@ def test_attention_vs_torch(cuda, Pq, Pk, masked):
     s = qh @ kh.transpose(-1, -2)
     s = s.masked_fill(mask[:, None, None, :], float('-inf'))
     ref = (torch.softmax(s, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(B, Pq, H * dh)
-    out = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), mask.to(torch.uint8).to(cuda) if masked else None, H)
-    assert util.rel_err(out.cpu(), ref) < 1e-4
+    for mode, tol in ((_lib.DZ_F32, 1e-4), (_lib.DZ_TF32, 3e-3)):
+        out = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), mask.to(torch.uint8).to(cuda) if masked else None, H, mode=mode)
+        assert util.rel_err(out.cpu(), ref) < tol, mode
 
 
 def test_linear_layernorm_groupmax(cuda):
