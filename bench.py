@@ -150,7 +150,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'Waymo-shape frames/sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * dt / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': 'CenterPoint 1-sweep %s, synthetic 180K-pt Waymo-range cloud, fp32, batch 1' % args.backbone},
+            'config': {'workload': 'CenterPoint 1-sweep %s, synthetic 180K-pt Waymo-range cloud, fp32, batch %d/GPU'
+                                   % (args.backbone, args.batch),
+                       'arm': 'oracle port of the reference algorithm on the host CPU (spconv cannot be installed here)'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d frames of the same workload, torch threads=%d' % (args.steps, cores)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}

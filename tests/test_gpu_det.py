@@ -343,3 +343,56 @@ def _assert_same_detections(got, want):
     diff = (gb[None, :, :] - wb[:, None, :]).abs() / (1.0 + 0.1 * wb[:, None, :].abs())
     nearest = diff.max(dim=2)[0].min(dim=1)
     assert nearest[0].max().item() < 1e-3
+
+
+def test_dynamic_vfe_into_backbone(cuda):
+    """BASELINE configs[2] path (multi-sweep): DynamicMeanVFE (key order b,x,y,z) -> VoxelResBackBone8x; the backbone builds
+    its grid index from the arbitrary-order coordinate list"""
+    from detzero_b200.det import cp_modules
+    cfg = util.model_cfg('VoxelResBackBone8x')
+    grid = [192, 192, 40]
+    vfe = cp_modules['DynamicMeanVFE'](model_cfg=cfg.VFE, num_point_features=6, voxel_size=util.VOXEL, grid_size=grid,
+                                       point_cloud_range=util.SMALL_RANGE)
+    bb = cp_modules['VoxelResBackBone8x'](model_cfg=cfg.BACKBONE_3D, input_channels=6, grid_size=grid).eval()
+    sd = weights.load_seeded(bb, 17)
+    bb = bb.to(cuda)
+    clouds = [util.clustered_cloud(30000, 71, c=6), util.clustered_cloud(18000, 72, c=6)]
+    pts = np.concatenate([np.pad(p, ((0, 0), (1, 0)), constant_values=b) for b, p in enumerate(clouds)]).astype(np.float32)
+    mean_ref, coords_ref = det_ref.dynamic_mean_vfe(pts, util.SMALL_RANGE, util.VOXEL, grid)
+    want = det_ref.voxel_backbone(sd, '', mean_ref, coords_ref.numpy(), bb.sparse_shape, 2, res=True)
+    bd = {'points': torch.from_numpy(pts).to(cuda), 'batch_size': 2}
+    with torch.no_grad():
+        bd = bb(vfe(bd))
+    m = int(bd['voxel_count'].item())
+    assert m == coords_ref.shape[0] and torch.equal(bd['voxel_coords'][:m].cpu(), coords_ref)
+    got = bd['encoded_spconv_tensor']
+    assert np.array_equal(got.indices.cpu().numpy(), want['out'].idx)
+    assert util.rel_err(got.features.cpu(), want['out'].f) < 1e-4
+
+
+def test_centerpoint_end_to_end_tf32(cuda):
+    """the default tensor-core configuration (TF32 sparse + dense convs): same detections as the fp32 oracle chain within
+    5 cm / 0.05 rad / 0.02 score for at least 90 % of the boxes (TF32 perturbs scores near the NMS / score thresholds)"""
+    from detzero_b200.det import build_network, load_data_to_gpu
+    from detzero_b200.det.dataset import SyntheticWaymoDataset, default_waymo_1sweep_cfg
+    dcfg = default_waymo_1sweep_cfg()
+    dcfg.POINT_CLOUD_RANGE = util.SMALL_RANGE
+    ds = SyntheticWaymoDataset(dcfg, util.CLASS_NAMES, training=False, num_frames=1, n_points=30000)
+    outs = {}
+    clouds = [util.clustered_cloud(30000, 61, c=6)]
+    for mode in ('fp32', 'tf32'):
+        cfg = util.model_cfg('VoxelBackBone8x', mode)
+        model = build_network(cfg, 3, ds).eval()
+        weights.load_seeded(model, 21)
+        model = model.to(cuda)
+        items = [ds.data_processor.forward(ds.point_feature_encoder.forward({'points': p.copy(), 'frame_id': '0'})) for p in clouds]
+        batch = load_data_to_gpu(ds.collate_batch(items), cuda)
+        with torch.no_grad():
+            outs[mode] = model(batch)[0][0]
+    a, b = outs['fp32'], outs['tf32']
+    assert abs(a['pred_boxes'].shape[0] - b['pred_boxes'].shape[0]) <= max(3, a['pred_boxes'].shape[0] // 20)
+    if a['pred_boxes'].shape[0]:
+        ga = torch.cat([a['pred_boxes'][:, :3], a['pred_boxes'][:, 6:7], a['pred_scores'][:, None] * 2.5, a['pred_labels'][:, None].float()], 1)
+        gb = torch.cat([b['pred_boxes'][:, :3], b['pred_boxes'][:, 6:7], b['pred_scores'][:, None] * 2.5, b['pred_labels'][:, None].float()], 1)
+        d = (ga[:, None, :] - gb[None, :, :]).abs().max(dim=2)[0].min(dim=1)[0]
+        assert (d < 0.05).float().mean().item() >= 0.9

@@ -222,3 +222,18 @@ def test_rotated_iou_restatement_matches_compiled_reference():
     out = torch.zeros(n, n)
     m.boxes_iou_bev_cpu(torch.from_numpy(b), torch.from_numpy(b), out)
     assert np.array_equal(out.numpy(), oracle.boxes_iou_bev(b, b))
+
+
+def test_yaml_config_builds_registry_model():
+    """the shipped YAML (same keys as the reference's centerpoint_1sweep.yaml) builds the detector through the registry"""
+    from detzero_b200.config import AttrDict, cfg_from_yaml_file
+    from detzero_b200.det import build_network
+    from detzero_b200.det.dataset import SyntheticWaymoDataset
+    root = os.path.join(os.path.dirname(HERE), 'detzero_b200')
+    cfg = cfg_from_yaml_file(os.path.join(root, 'cfgs', 'det_model_cfgs', 'centerpoint_1sweep.yaml'), AttrDict())
+    assert cfg.DATA_CONFIG.POINT_CLOUD_RANGE == [-75.2, -75.2, -2, 75.2, 75.2, 4]
+    ds = SyntheticWaymoDataset(cfg.DATA_CONFIG, cfg.CLASS_NAMES, training=False, num_frames=1, n_points=1000)
+    model = build_network(cfg.MODEL, len(cfg.CLASS_NAMES), ds)
+    names = [type(m).__name__ for m in model.module_list]
+    assert names == ['MeanVFE', 'VoxelResBackBone8x', 'HeightCompression', 'BaseBEVBackbone', 'CenterHead']
+    assert model.backbone3d.sparse_shape == [41, 1504, 1504] and model.vfe.max_voxels == 200000
