@@ -47,6 +47,9 @@ def parse():
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--no-schedule', action='store_true', help='run the tensor-core sparse convs without the mask-grouped tile schedule')
+    ap.add_argument('--layer-times', action='store_true', help='print per-layer sparse-conv times of the traced frame to stderr')
+    ap.add_argument('--modules', type=int, default=0, help='diagnostic: graph-replay time of only the first N modules of the detector (stderr, then exit)')
     ap.add_argument('--stage-times', action='store_true', help='print a per-stage device time table to stderr')
     return ap.parse_args()
 
@@ -55,6 +58,8 @@ def make_model_cfg(backbone, mode, sp_mode):
     from tests import util
     cfg = util.model_cfg(backbone, mode)
     cfg.BACKBONE_3D.COMPUTE_MODE = sp_mode
+    if os.environ.get('DZ_NO_OVERLAP'):
+        cfg.BACKBONE_3D.OVERLAP_RULEBOOKS = False      # diagnostic: rulebooks inline on the main stream
     return cfg
 
 
@@ -180,6 +185,12 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     ds, batches = build_inputs(args.batch)
+    if os.environ.get('DZ_SIDE_PRIO') == '0':
+        from detzero_b200.det import backbone3d as _b3
+        _b3._Backbone8xBase.SIDE_STREAM_HIGH_PRIORITY = False
+    if args.no_schedule:
+        from detzero_b200.spconv import pytorch as _sp
+        _sp._SparseConv.SCHEDULE_TILES = False
     model = build_network(make_model_cfg(args.backbone, args.mode, args.sp_mode), 3, ds).eval()
     weights.load_seeded(model, 3)
     model = model.to(dev)
@@ -250,6 +261,47 @@ def main():
             step_e2e(i)
     torch.cuda.synchronize()
 
+    if args.stage_times and rank == 0:
+        # main-stream device time per module of the eager frame (rulebook side streams overlap the backbone's convs)
+        names = [type(m).__name__ for m in model.module_list]
+        acc = [0.0] * len(names)
+        reps = 6
+        with torch.no_grad():
+            for f in range(reps + 2):
+                bd = batch_dict(f, dev_pts[f % NUM_CLOUDS])
+                flush.zero_()
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                evs[0].record()
+                for k, m in enumerate(model.module_list):
+                    bd = m(bd)
+                    evs[k + 1].record()
+                torch.cuda.synchronize()
+                if f >= 2:
+                    for k in range(len(names)):
+                        acc[k] += evs[k].elapsed_time(evs[k + 1]) / reps
+        print('stage times (eager, us/frame): ' + ', '.join('%s %.0f' % (n, 1000 * t) for n, t in zip(names, acc)) +
+              ' | total %.0f' % (1000 * sum(acc)), file=sys.stderr)
+
+    if args.modules and rank == 0:
+        full = list(model.module_list)
+        for nmod in range(1, len(full) + 1):
+            model.module_list = full[:nmod]
+            sp = dev_pts[0].clone()
+            gg, _ = model.capture_graph(batch_dict(0, sp), warmup=1)
+            ts = []
+            for i in range(13):
+                flush.zero_()
+                sp.copy_(dev_pts[i % NUM_CLOUDS])
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); gg.replay(); e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            print('graph replay of the first %d modules (.. %s): median %.0f us' % (nmod, type(full[nmod - 1]).__name__, 1000 * ts[len(ts) // 2]), file=sys.stderr)
+        model.module_list = full
+        return
+
     if not args.no_graph:
         static_pts = dev_pts[0].clone()
         ops.reset_launch_count()
@@ -318,7 +370,21 @@ def sparse_conv_roofline(model, step_fn, args, dev):
     ops.enable_spconv_trace(False)
     tot_bytes, tot_ms, tot_flops = 0.0, 0.0, 0.0
     for r in rec:
-        pairs = int((r['nbr'][:, :r['n_out']] >= 0).sum().item())
+        if r['nbr'].shape[1] == 32 and r['nbr'].shape[0] != r['K']:      # tensor-core launch: row-major table (cap, 32)
+            valid = r['nbr'][:r['n_out'], :r['K']].t() >= 0
+            if r['row_order'] is not None:
+                valid = valid[:, r['row_order'][:r['n_out']].long()]        # tile order (for the offsets/tile statistic)
+        else:
+            valid = r['nbr'][:, :r['n_out']] >= 0
+        pairs = int(valid.sum().item())
+        if args.layer_times:
+            T = (r['n_out'] + 127) // 128
+            v = torch.zeros((valid.shape[0], T * 128), dtype=torch.bool, device=valid.device)
+            v[:, :r['n_out']] = valid
+            touched = int(v.view(valid.shape[0], T, 128).any(2).sum().item())
+            print('spconv layer K=%d cin=%d cout=%d n_out=%d pairs=%d offsets/tile=%.1f scheduled=%s  %.1f us' % (
+                r['K'], r['cin'], r['cout'], r['n_out'], pairs, touched / max(T, 1), r['row_order'] is not None,
+                1000 * r['start'].elapsed_time(r['end'])), file=sys.stderr)
         K, cin, cout = r['K'], r['cin'], r['cout']
         b = (r['n_in'] * cin + r['n_out'] * cout) * 4 + pairs * 8 + K * cin * cout * 4 + (r['n_out'] * cout * 4 if r['residual'] else 0)
         tot_bytes += b

@@ -7,4 +7,6 @@ struct Conv2dParams {
     int Ho, Wo, cout;
     int OH, OW, os, oy0, ox0;        // physical output: pixel (ho*os+oy0, wo*os+ox0) of an (OH, OW) map
     int out_coff, out_cstride, relu;
+    int dbg;                         // experiment switches (DZ_CONV2D_DBG): 1 = skip weight loads, 2 = skip activation loads (timing only)
+    int tma_store;                   // epilogue through shared memory + TMA store (tensor-core kernel, os == 1)
 };

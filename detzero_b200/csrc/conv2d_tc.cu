@@ -11,6 +11,7 @@
 // a ring of mbarrier-guarded stages overlaps TMA with MMA; 4 epilogue warps read TMEM (tcgen05.ld), apply the
 // folded BatchNorm / bias / ReLU and write NHWC rows (optionally into a channel slice / strided pixels: fused
 // torch.cat and ConvTranspose2d with kernel == stride).
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv2d.cuh"
 #include "tc.cuh"
@@ -43,10 +44,16 @@ struct CtCfg {
 
 // MT = output patches per CTA (stacked in y): the weight tile of every k-step is shared by MT accumulators, which cuts the
 // L2->SM bytes per MMA (the kernel is bound by the ~34 B/clk/SM an SM can pull from L2, not by the tensor pipe)
+__device__ long long g_ct_trace[64];          // DZ_CONV2D_DBG & 4: clock stamps of CTA 0 (tools/bench_conv2d.py)
+extern "C" int dz_debug_conv2d_trace(long long* host) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host, g_ct_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
+}
+
 template <int BN, int MT>
 __global__ void __launch_bounds__(CT_THREADS, 1)
-k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Conv2dParams p, int tiles_x,
-              int tiles_y) {
+k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+              Conv2dParams p, int tiles_x, int tiles_y) {
     using Cfg = CtCfg<BN, MT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -56,6 +63,8 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool tr = (p.dbg & 4) && blockIdx.x == 0 && blockIdx.y == 0;
+    if (tr && threadIdx.x == 0) g_ct_trace[0] = clock64();
     int mt = blockIdx.x;
     const int tx0 = (mt % tiles_x) * CT_TW; mt /= tiles_x;
     const int ty0 = (mt % tiles_y) * (CT_TH * MT);
@@ -67,6 +76,7 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
+        if (p.tma_store) tc::prefetch_tmap(&tmO);
         for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
@@ -76,6 +86,7 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tr && threadIdx.x == 0) g_ct_trace[1] = clock64();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -86,12 +97,15 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 unsigned char* sb = sa + MT * CT_A_BYTES;
                 const int tap = it / cchunks, cc = it - tap * cchunks;
                 const int r = tap / p.KW, sx = tap - r * p.KW;
-                tc::mbar_arrive_expect_tx(full + s, Cfg::STAGE_BYTES);
+                const bool ldA = !(p.dbg & 2) || it < Cfg::STAGES, ldB = !(p.dbg & 1) || it < Cfg::STAGES;
+                tc::mbar_arrive_expect_tx(full + s, (ldA ? MT * CT_A_BYTES : 0) + (ldB ? Cfg::B_BYTES : 0));
+                if (ldA) {
 #pragma unroll
-                for (int m = 0; m < MT; ++m)
-                    tc::tma_load_4d(sa + m * CT_A_BYTES, &tmA, full + s, cc * CT_BK, tx0 * p.stride + sx - p.pad,
-                                    (ty0 + m * CT_TH) * p.stride + r - p.pad, b);
-                tc::tma_load_2d(sb, &tmB, full + s, tap * p.cin + cc * CT_BK, n0);
+                    for (int m = 0; m < MT; ++m)
+                        tc::tma_load_4d(sa + m * CT_A_BYTES, &tmA, full + s, cc * CT_BK, tx0 * p.stride + sx - p.pad,
+                                        (ty0 + m * CT_TH) * p.stride + r - p.pad, b);
+                }
+                if (ldB) tc::tma_load_2d(sb, &tmB, full + s, tap * p.cin + cc * CT_BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -99,7 +113,9 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             constexpr uint32_t idesc = tc::instr_desc(2, 128, BN < 16 ? 16 : BN);
             for (int it = 0; it < iters; ++it) {
                 const int s = it % Cfg::STAGES;
+                if (tr && it < 20) g_ct_trace[8 + it * 2] = clock64();
                 tc::mbar_wait(full + s, (it / Cfg::STAGES) & 1);
+                if (tr && it < 20) g_ct_trace[9 + it * 2] = clock64();
                 tc::tcgen05_fence_after();
                 const uint32_t sa = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
                 const uint64_t bdesc = tc::smem_desc_sw128(sa + MT * CT_A_BYTES);
@@ -114,6 +130,7 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 tc::mma_commit(empty + s);                      // frees the stage once these MMAs have read it
             }
             tc::mma_commit(tmem_full);
+            if (tr) g_ct_trace[2] = clock64();
         }
     } else {
         // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
@@ -121,6 +138,7 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int row = q * 32 + lane;                          // pixel index inside the 8x16 patch
         tc::mbar_wait(tmem_full, 0);
         tc::tcgen05_fence_after();
+        if (tr && threadIdx.x == 64) g_ct_trace[3] = clock64();
 #pragma unroll 1
         for (int mc = 0; mc < MT * BN; mc += 32) {
             const int m = mc / BN, c0 = mc % BN;
@@ -129,7 +147,35 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             float* orow = p.out + (((size_t)b * p.OH + (y * p.os + p.oy0)) * p.OW + (x * p.os + p.ox0)) * p.out_cstride + p.out_coff;
             float v[32];
             tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mc, v);
-            if (valid) {
+            if (p.tma_store) {
+                // The strided per-pixel stores of the direct path (32 lanes -> 32 different lines per instruction) made the
+                // epilogue as long as the main loop.  Here the warp's 32 pixels x 32 channels go to the (now idle) pipeline
+                // buffers in the 128B-swizzled box layout and ONE TMA store per warp writes them (edge tiles clipped by the
+                // tensor map, channel range clipped at out_coff + cout).
+                unsigned char* stg = smem + (mc / 32) * CT_A_BYTES + q * 4096;        // 32 rows x 128 B
+                const uint32_t stg_u = tc::smem_u32(stg) + (uint32_t)((lane >> 3) * 1024 + (lane & 7) * 128);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + c0 + j;
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (n < p.cout) {
+                        if (p.scale) { float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n)); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+                        if (p.shift) { float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n)); o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w; }
+                    }
+                    if (p.relu) {
+                        o.x = tc::rna_tf32(fmaxf(o.x, 0.f)); o.y = tc::rna_tf32(fmaxf(o.y, 0.f));
+                        o.z = tc::rna_tf32(fmaxf(o.z, 0.f)); o.w = tc::rna_tf32(fmaxf(o.w, 0.f));
+                    }
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4)),
+                                 "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                }
+                tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
+                __syncwarp();
+                if (lane == 0 && n0 + c0 < p.cout) {
+                    tc::tma_store_4d(&tmO, stg, p.out_coff + n0 + c0, tx0, ty0 + m * CT_TH + q * 2, b);
+                    tc::tma_store_commit();
+                }
+            } else if (valid) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int n = n0 + c0 + j;
@@ -144,13 +190,15 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
         }
     }
+    if (p.tma_store && warp >= 2 && lane == 0) tc::tma_store_wait_read();      // the stores must have read the staging buffers
     tc::tcgen05_fence_before();
     __syncthreads();
+    if (tr && threadIdx.x == 0) g_ct_trace[4] = clock64();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 template <int BN, int MT>
-static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t st) {
     using Cfg = CtCfg<BN, MT>;
     static bool configured = false;
     if (!configured) {
@@ -159,13 +207,15 @@ static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUte
     }
     int tiles_x = dz_cdiv(p.Wo, CT_TW), tiles_y = dz_cdiv(p.Ho, CT_TH * MT);
     dim3 grid(tiles_x * tiles_y * p.B, dz_cdiv(p.cout, BN));
-    k_conv2d_tf32<BN, MT><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, p, tiles_x, tiles_y);
+    static_assert((MT * BN / 32) * CT_A_BYTES <= Cfg::STAGES * Cfg::STAGE_BYTES || MT * BN < 32, "epilogue staging must fit in the pipeline buffers");
+    k_conv2d_tf32<BN, MT><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmO, p, tiles_x, tiles_y);
     DZ_LAUNCH_CHECK();
     return DZ_OK;
 }
 
 // p.w must be in (cout, KH, KW, cin) layout for this path
-int dz_conv2d_fwd_tc(const Conv2dParams& p, int mode, cudaStream_t st) {
+int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
+    Conv2dParams p = p_in;
     if (mode != DZ_TF32) { dz_set_error("dz_conv2d_fwd: tensor-core mode %d not built (tf32 only)", mode); return DZ_ERR_UNSUPPORTED; }
     if (p.cin % CT_BK != 0 || p.in_cstride % 4 != 0 || p.cout % 4 != 0 || p.out_cstride % 4 != 0 || p.out_coff % 4 != 0) {
         dz_set_error("dz_conv2d_fwd(tf32): needs cin %% 32 == 0 and 16-byte aligned channel slices (cin=%d cout=%d)", p.cin, p.cout);
@@ -195,14 +245,28 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p, int mode, cudaStream_t st) {
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
+    CUtensorMap tmO = tmB;
+    static const int no_tma_store = getenv("DZ_CONV2D_NO_TMA_STORE") ? 1 : 0;
+    p.tma_store = (!no_tma_store && p.os == 1 && p.oy0 == 0 && p.ox0 == 0 && p.OH == p.Ho && p.OW == p.Wo && bn >= 32 &&
+                   (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
+    if (p.tma_store) {
+        // channels [0, out_coff + cout) of the (possibly wider, concatenated) output tensor: stores past cout are clipped
+        cuuint64_t dims[4] = {(cuuint64_t)(p.out_coff + p.cout), (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.out_cstride * 4, (cuuint64_t)p.OW * p.out_cstride * 4, (cuuint64_t)p.OH * p.OW * p.out_cstride * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)CT_TW, 2, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
     // two stacked patches per CTA when there are enough tiles to still fill the GPU (the weight tile is then loaded once
     // for 256 output pixels)
     const long long tiles1 = (long long)dz_cdiv(p.Wo, CT_TW) * dz_cdiv(p.Ho, CT_TH) * p.B * dz_cdiv(p.cout, bn);
     const bool two = tiles1 >= 2 * DZ_NUM_SMS - 16;
     switch (bn) {
-        case 128: return two ? launch_tf32<128, 2>(p, tmA, tmB, st) : launch_tf32<128, 1>(p, tmA, tmB, st);
-        case 64: return two ? launch_tf32<64, 2>(p, tmA, tmB, st) : launch_tf32<64, 1>(p, tmA, tmB, st);
-        default: return two ? launch_tf32<32, 2>(p, tmA, tmB, st) : launch_tf32<32, 1>(p, tmA, tmB, st);
+        case 128: return two ? launch_tf32<128, 2>(p, tmA, tmB, tmO, st) : launch_tf32<128, 1>(p, tmA, tmB, tmO, st);
+        case 64: return two ? launch_tf32<64, 2>(p, tmA, tmB, tmO, st) : launch_tf32<64, 1>(p, tmA, tmB, tmO, st);
+        default: return two ? launch_tf32<32, 2>(p, tmA, tmB, tmO, st) : launch_tf32<32, 1>(p, tmA, tmB, tmO, st);
     }
 }
 

@@ -180,16 +180,17 @@ static int launch_f32(const float* in, int cin, const int32_t* nbr, int K, int n
     return DZ_OK;
 }
 
-int dz_spconv_fwd_tc(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out, int out_cap,
+int dz_spconv_fwd_tc(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int32_t* order, const int* d_n_out, int out_cap,
                      const float* weight, const float* scale, const float* shift, const float* residual, int relu,
                      float* out, int cout, int mode, cudaStream_t st);
 
-extern "C" int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
+extern "C" int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int32_t* row_order, const int* d_n_out,
                              int out_cap, const float* weight, const float* scale, const float* shift,
                              const float* residual, int relu, float* out, int cout, int mode, dz_stream_t stream) {
     DZ_CHECK_ARG(in && nbr && d_n_out && weight && out && cin >= 1 && K >= 1 && out_cap >= 1 && nbr_cap >= out_cap);
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == DZ_F32) {
+        if (row_order) { dz_set_error("dz_spconv_fwd: row_order is for the tensor-core modes (the fp32 kernel compacts per offset itself)"); return DZ_ERR_UNSUPPORTED; }
         switch (cout) {
             case 16: return launch_f32<16>(in, cin, nbr, K, nbr_cap, d_n_out, out_cap, weight, scale, shift, residual, relu, out, st);
             case 32: return launch_f32<32>(in, cin, nbr, K, nbr_cap, d_n_out, out_cap, weight, scale, shift, residual, relu, out, st);
@@ -198,5 +199,5 @@ extern "C" int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_
             default: dz_set_error("dz_spconv_fwd: cout=%d unsupported (16/32/64/128)", cout); return DZ_ERR_UNSUPPORTED;
         }
     }
-    return dz_spconv_fwd_tc(in, cin, in_rows, nbr, K, nbr_cap, d_n_out, out_cap, weight, scale, shift, residual, relu, out, cout, mode, st);
+    return dz_spconv_fwd_tc(in, cin, in_rows, nbr, K, nbr_cap, row_order, d_n_out, out_cap, weight, scale, shift, residual, relu, out, cout, mode, st);
 }

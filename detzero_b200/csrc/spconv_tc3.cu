@@ -32,12 +32,13 @@ struct S3Cfg {
 template <int CIN_PAD, int COUT>
 __global__ void __launch_bounds__(S3Cfg<COUT>::THREADS, 1)
 k_spconv_3xtf32(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ in, int cin,
-                const int32_t* __restrict__ nbr, int K, int nbr_cap, const int* __restrict__ d_n_out, int out_cap,
+                const int32_t* __restrict__ nbr, int K, int nbr_cap, const int32_t* __restrict__ order, const int* __restrict__ d_n_out, int out_cap,
                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ residual, int relu,
                 float* __restrict__ out) {
     using Cfg = S3Cfg<COUT>;
     const int n = min(*d_n_out, out_cap);
-    const int row0 = blockIdx.x * S3_ROWS;
+    // under a tile schedule CTAs take the tiles heaviest-first (launch order ~ blockIdx order): order[nbr_cap + i]
+    const int row0 = (order ? __ldg(order + nbr_cap + blockIdx.x) : (int)blockIdx.x) * S3_ROWS;
     if (row0 >= n) return;
 
     extern __shared__ unsigned char smem_raw[];
@@ -66,9 +67,20 @@ k_spconv_3xtf32(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     __syncthreads();
     if (warp < 4) {
         const int r = row0 + threadIdx.x;
+        // table row of this tile position (row-major table, one 128-byte line per output row; order[pos] under a schedule)
+        const int src = r < n ? (order ? __ldg(order + r) : r) : -1;
         int v[S3_KMAX];
+        {
+            int w[28];
+            const int4* rowp = reinterpret_cast<const int4*>(nbr) + (size_t)(src < 0 ? 0 : src) * 8;
 #pragma unroll
-        for (int k = 0; k < S3_KMAX; ++k) v[k] = (k < K && r < n) ? __ldg(nbr + (size_t)k * nbr_cap + r) : -1;
+            for (int q = 0; q < 7; ++q) {
+                const int4 t4 = src >= 0 ? __ldg(rowp + q) : make_int4(-1, -1, -1, -1);
+                w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < S3_KMAX; ++k) v[k] = k < K ? w[k] : -1;
+        }
         unsigned mine = 0;
 #pragma unroll
         for (int k = 0; k < S3_KMAX; ++k) {
@@ -154,7 +166,8 @@ k_spconv_3xtf32(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     if (warp < 4) {
         // ================= epilogue =================
         const int q = warp;
-        const int r = row0 + q * 32 + lane;
+        const int pos = row0 + q * 32 + lane;       // tile position; the output row is order[pos] under a tile schedule
+        const int r = pos < n ? (order ? __ldg(order + pos) : pos) : n;
         tc::mbar_wait(tmem_full, 0);
         tc::tcgen05_fence_after();
 #pragma unroll 1
@@ -208,7 +221,7 @@ k_spconv_3xtf32(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
 
 template <int CIN_PAD, int COUT>
 static int launch3(const CUtensorMap& hi, const CUtensorMap& lo, const float* in, int cin, const int32_t* nbr, int K, int nbr_cap,
-                   const int* d_n_out, int out_cap, const float* scale, const float* shift, const float* residual, int relu, float* out,
+                   const int32_t* order, const int* d_n_out, int out_cap, const float* scale, const float* shift, const float* residual, int relu, float* out,
                    cudaStream_t st) {
     using Cfg = S3Cfg<COUT>;
     static bool configured = false;
@@ -216,14 +229,14 @@ static int launch3(const CUtensorMap& hi, const CUtensorMap& lo, const float* in
         DZ_CUDA(cudaFuncSetAttribute(k_spconv_3xtf32<CIN_PAD, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
-    k_spconv_3xtf32<CIN_PAD, COUT><<<dz_cdiv(out_cap, S3_ROWS), Cfg::THREADS, Cfg::SMEM, st>>>(hi, lo, in, cin, nbr, K, nbr_cap, d_n_out, out_cap,
+    k_spconv_3xtf32<CIN_PAD, COUT><<<dz_cdiv(out_cap, S3_ROWS), Cfg::THREADS, Cfg::SMEM, st>>>(hi, lo, in, cin, nbr, K, nbr_cap, order, d_n_out, out_cap,
                                                                                              scale, shift, residual, relu, out);
     DZ_LAUNCH_CHECK();
     return DZ_OK;
 }
 
 // weight layout: (2, cout, K*cin_pad): [0] = RN_tf32(W), [1] = RN_tf32(W - W_hi)
-int dz_spconv_fwd_tc3(const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out, int out_cap,
+int dz_spconv_fwd_tc3(const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int32_t* order, const int* d_n_out, int out_cap,
                       const float* weight, const float* scale, const float* shift, const float* residual, int relu, float* out,
                       int cout, cudaStream_t st) {
     if (K > S3_KMAX) { dz_set_error("dz_spconv_fwd(tf32x3): K=%d > 27", K); return DZ_ERR_UNSUPPORTED; }
@@ -242,7 +255,7 @@ int dz_spconv_fwd_tc3(const float* in, int cin, const int32_t* nbr, int K, int n
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(W) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
-#define DZ_S3(CP, CO) return launch3<CP, CO>(tm[0], tm[1], in, cin, nbr, K, nbr_cap, d_n_out, out_cap, scale, shift, residual, relu, out, st)
+#define DZ_S3(CP, CO) return launch3<CP, CO>(tm[0], tm[1], in, cin, nbr, K, nbr_cap, order, d_n_out, out_cap, scale, shift, residual, relu, out, st)
     if (cin_pad == 8 && cout == 16) DZ_S3(8, 16);
     if (cin_pad == 16 && cout == 16) DZ_S3(16, 16);
     if (cin_pad == 16 && cout == 32) DZ_S3(16, 32);

@@ -71,29 +71,41 @@ class _Backbone8xBase(nn.Module):
                 order.append(m)
         return order
 
+    SIDE_STREAM_HIGH_PRIORITY = True
+
     def prebuild_rulebooks(self, x0):
         """Build all rulebooks of the frame on a side stream while the feature convolutions run on the main stream:
         rulebooks depend only on coordinates, so the whole chain (spconv2 -> subm2 -> spconv3 -> ...) can run ahead of the
         features.  Every conv waits on its own rulebook's event.  Captured as parallel branches by CUDA graphs."""
         main = torch.cuda.current_stream()
         if getattr(self, '_side', None) is None or self._side.device != x0._feat.device:
-            self._side = torch.cuda.Stream(device=x0._feat.device)
-        side = self._side
+            # high priority: the short rulebook kernels must not queue behind the conv grids that fill every SM
+            prio = -1 if self.SIDE_STREAM_HIGH_PRIORITY else 0
+            self._side = torch.cuda.Stream(device=x0._feat.device, priority=prio)
+            self._side2 = torch.cuda.Stream(device=x0._feat.device, priority=prio)
+        side, side2 = self._side, self._side2
         side.wait_stream(main)
+        side2.wait_stream(main)
         events = {}
-        with torch.cuda.stream(side):
-            t = x0
-            for conv in self._first_convs():
-                rule = conv._rule(t)
+        t = x0
+        for conv in self._first_convs():
+            with torch.cuda.stream(side):               # the coordinate chain: rulebook -> next level's sites -> rulebook ...
+                rule = conv._rule(t, schedule=False)
                 ev = torch.cuda.Event()
                 ev.record(side)
-                events[conv.indice_key] = ev
-                if not conv.subm:                       # coordinates-only view of the strided conv's output sites
+            with torch.cuda.stream(side2):              # the tile schedules hang off the chain without lengthening it
+                side2.wait_event(ev)
+                conv._schedule(rule, t)
+                ev2 = torch.cuda.Event()
+                ev2.record(side2)
+            events[conv.indice_key] = ev2
+            if not conv.subm:                           # coordinates-only view of the strided conv's output sites
+                with torch.cuda.stream(side):
                     t = spconv.SparseConvTensor(t._feat[:1].new_empty((rule.out_cap, 1)), rule.out_idx, rule.out_dhw, t.batch_size,
                                                 indice_dict=t.indice_dict, count=rule.d_n_out, n_host=None, index=rule.out_index)
-                    t._producer = conv
+                t._producer = conv
         x0.indice_dict['__events__'] = events
-        x0.indice_dict['__side__'] = side
+        x0.indice_dict['__side__'] = (side, side2)
 
     def forward(self, batch_dict):
         if self.training:
@@ -109,7 +121,8 @@ class _Backbone8xBase(nn.Module):
         out = self.conv_out(x_conv4)
         side = x0.indice_dict.pop('__side__', None)
         if side is not None:
-            torch.cuda.current_stream().wait_stream(side)            # join (all rulebook memory is safe to reuse afterwards)
+            for s in side:
+                torch.cuda.current_stream().wait_stream(s)           # join (all rulebook memory is safe to reuse afterwards)
             x0.indice_dict.pop('__events__', None)
         batch_dict.update({'encoded_spconv_tensor': out, 'encoded_spconv_tensor_stride': 8})
         batch_dict.update({'multi_scale_3d_features': {'x_conv1': x_conv1, 'x_conv2': x_conv2, 'x_conv3': x_conv3,

@@ -18,6 +18,7 @@ def _stream():
 
 
 _launches = 0
+_skip_spconv = bool(__import__('os').environ.get('DZ_SKIP_SPCONV'))
 _trace = None
 
 
@@ -138,34 +139,66 @@ def voxelize_dynamic_mean(points, c, B, pc_range, voxel_size, grid_xyz, cap):
     return feats, coords, d_m
 
 
-def rulebook_subm(coords, d_n, cap, index, ksize):
+def new_sched_ws(cap, device):
+    """scratch a rulebook kernel fills with the mask digests + scanned histogram its tile schedule is built from (one per
+    rulebook: the schedule is built later, on another stream)"""
+    return torch.empty(int(lib().dz_rulebook_schedule_ws_bytes(cap)), dtype=torch.uint8, device=device)
+
+
+def rulebook_subm(coords, d_n, cap, index, ksize, layout='k', sched_ws=None):
+    """layout 'k': k-major (K, cap) table (exact-fp32 kernel, parity tests); 'row': row-major (cap, 32) table for the
+    tensor-core kernels; 'both': (nbr, tab).  sched_ws (row/both only): also leave the tile-schedule digests there."""
     K = ksize[0] * ksize[1] * ksize[2]
-    nbr = torch.empty((K, cap), dtype=torch.int32, device=coords.device)
+    nbr = torch.empty((K, cap), dtype=torch.int32, device=coords.device) if layout in ('k', 'both') else None
+    tab = torch.empty((cap, 32), dtype=torch.int32, device=coords.device) if layout in ('row', 'both') else None
     check(lib().dz_rulebook_subm(_p(coords), _p(d_n), cap, index.B, *index.dhw, iarr(ksize), _p(index.bitmap),
-                                 _p(index.prefix), _p(index.perm), _p(nbr), _stream()), 'rulebook_subm')
+                                 _p(index.prefix), _p(index.perm), _p(nbr), _p(tab), _p(sched_ws), _stream()), 'rulebook_subm')
+    _count(1 if sched_ws is None else 2)
+    return nbr if layout == 'k' else tab if layout == 'row' else (nbr, tab)
+
+
+def rulebook_schedule(tab, d_n, sched_ws):
+    """tile schedule for the tensor-core conv from the scratch the rulebook call filled: returns `order`
+    (cap + ceil(cap/128),) = row order | tile launch order; see dz_rulebook_schedule"""
+    _need_cuda(tab)
+    cap = tab.shape[0]
+    order = torch.empty(cap + (cap + 127) // 128, dtype=torch.int32, device=tab.device)
+    check(lib().dz_rulebook_schedule(_p(tab), cap, _p(d_n), _p(order), _p(sched_ws), sched_ws.numel(), _stream()), 'rulebook_schedule')
     _count(1)
-    return nbr
+    return order
+
+
+def table_to_rows(nbr):
+    """k-major (K, cap) table -> the row-major (cap, 32) layout of the tensor-core kernels (host-side helper for callers that
+    only hold the k-major form; the rulebook kernels write either layout directly)"""
+    K, cap = nbr.shape
+    tab = torch.full((cap, 32), -1, dtype=torch.int32, device=nbr.device)
+    tab[:, :K] = nbr.t()
+    tab[:, 27] = ((nbr >= 0).to(torch.int64) << torch.arange(K, device=nbr.device)[:, None]).sum(0).to(torch.int32)
+    tab[:, 28:] = 0
+    return tab
 
 
 def conv_out_dhw(in_dhw, ksize, stride, pad):
     return [(in_dhw[d] + 2 * pad[d] - (ksize[d] - 1) - 1) // stride[d] + 1 for d in range(3)]
 
 
-def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap):
+def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap, layout='k', sched_ws=None):
     dev = coords.device
     out_dhw = conv_out_dhw(in_index.dhw, ksize, stride, pad)
     out_index = GridIndex(in_index.B, out_dhw, dev)
     K = ksize[0] * ksize[1] * ksize[2]
-    out_coords = torch.zeros((out_cap, 4), dtype=torch.int32, device=dev)
-    d_n_out = torch.zeros(1, dtype=torch.int32, device=dev)
-    nbr = torch.empty((K, out_cap), dtype=torch.int32, device=dev)
+    out_coords = torch.empty((out_cap, 4), dtype=torch.int32, device=dev)      # rows >= the count are never read
+    d_n_out = torch.empty(1, dtype=torch.int32, device=dev)                    # written by the rank scan
+    nbr = torch.empty((K, out_cap), dtype=torch.int32, device=dev) if layout in ('k', 'both') else None
+    tab = torch.empty((out_cap, 32), dtype=torch.int32, device=dev) if layout in ('row', 'both') else None
     ws = workspace(scan_ws_bytes(out_index.words), dev, 'rulebook')      # own scratch: rulebooks run on a side stream
     check(lib().dz_rulebook_conv(_p(coords), _p(d_n), in_cap, in_index.B, iarr(in_index.dhw), iarr(ksize), iarr(stride),
                                  iarr(pad), _p(in_index.bitmap), _p(in_index.prefix), _p(in_index.perm), _p(out_coords),
-                                 _p(d_n_out), out_cap, _p(out_index.bitmap), _p(out_index.prefix), _p(nbr), _p(ws),
-                                 ws.numel(), _stream()), 'rulebook_conv')
-    _count(6)
-    return out_coords, d_n_out, out_index, nbr, out_dhw
+                                 _p(d_n_out), out_cap, _p(out_index.bitmap), _p(out_index.prefix), _p(nbr), _p(tab), _p(ws),
+                                 ws.numel(), _p(sched_ws), _stream()), 'rulebook_conv')
+    _count(6 if sched_ws is None else 7)
+    return out_coords, d_n_out, out_index, (nbr if layout == 'k' else tab if layout == 'row' else (nbr, tab)), out_dhw
 
 
 def pack_spconv_weight(w, mode):
@@ -194,17 +227,24 @@ def round_tf32(t):
 
 
 def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None,
-               d_n_in=None, kshape=None):
-    """feats (in_cap, cin); nbr (K, nbr_cap); weight_packed per pack_spconv_weight; kshape = (K, cin, cout)"""
+               d_n_in=None, kshape=None, row_order=None):
+    """feats (in_cap, cin); weight_packed per pack_spconv_weight; kshape = (K, cin, cout).
+    nbr: k-major (K, cap) table for DZ_F32; row-major (cap, 32) table for the tensor-core modes (a k-major table is
+    converted on the fly); row_order: tile schedule from rulebook_schedule (tensor-core modes)"""
     _need_cuda(feats, nbr, weight_packed)
     K, cin, cout = kshape if kshape is not None else weight_packed.shape
-    assert feats.shape[1] == cin and nbr.shape[0] == K
+    if mode != _lib.DZ_F32 and not (nbr.shape[1] == 32 and nbr.shape[0] != K):
+        nbr = table_to_rows(nbr)
+    assert feats.shape[1] == cin and (nbr.shape[0] == K if mode == _lib.DZ_F32 else nbr.shape[1] == 32)
     if out is None:
         out = torch.empty((out_cap, cout), dtype=torch.float32, device=feats.device)
+    if _skip_spconv:                      # timing experiment (DZ_SKIP_SPCONV=1): what is left when the conv kernels cost nothing
+        return out
     if _trace is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, feats.shape[0], _p(nbr), K, nbr.shape[1], _p(d_n_out), out_cap,
+    check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, feats.shape[0], _p(nbr), K, nbr.shape[1] if mode == _lib.DZ_F32 else nbr.shape[0],
+                              _p(row_order), _p(d_n_out), out_cap,
                               _p(_f32c(weight_packed)), _p(scale), _p(shift), _p(residual), int(relu), _p(out), cout,
                               mode, _stream()), 'spconv_fwd')
     _count(1)
@@ -213,7 +253,7 @@ def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residu
         torch.cuda.synchronize()
         n_out = min(int(d_n_out.item()), out_cap)
         n_in = min(int(d_n_in.item()), feats.shape[0]) if d_n_in is not None else n_out
-        _trace.append(dict(start=ev0, end=ev1, K=K, cin=cin, cout=cout, n_in=n_in, n_out=n_out, nbr=nbr,
+        _trace.append(dict(start=ev0, end=ev1, K=K, cin=cin, cout=cout, n_in=n_in, n_out=n_out, nbr=nbr, row_order=row_order,
                            residual=residual is not None))
     return out
 

@@ -138,14 +138,19 @@ def fold_bn(bn, conv_bias, device=None):
 
 
 class _RuleSubm:
-    def __init__(self, nbr):
-        self.nbr = nbr
+    def __init__(self, nbr, tab):
+        self.nbr = nbr             # k-major table (exact-fp32 kernel) or None
+        self.tab = tab             # row-major table (tensor-core kernels) or None
+        self.order = None          # tile schedule (tensor-core kernels)
+        self.sched_ws = None       # mask digests + histogram left by the rulebook kernel
 
 
 class _RuleConv:
-    def __init__(self, out_idx, d_n_out, out_index, nbr, out_dhw, out_cap):
-        self.out_idx, self.d_n_out, self.out_index, self.nbr, self.out_dhw, self.out_cap = \
-            out_idx, d_n_out, out_index, nbr, out_dhw, out_cap
+    def __init__(self, out_idx, d_n_out, out_index, tables, out_dhw, out_cap):
+        self.out_idx, self.d_n_out, self.out_index, self.out_dhw, self.out_cap = out_idx, d_n_out, out_index, out_dhw, out_cap
+        self.nbr, self.tab = tables
+        self.order = None
+        self.sched_ws = None
 
 
 class _SparseConv(SparseModule):
@@ -155,6 +160,8 @@ class _SparseConv(SparseModule):
     #: is detected (device count > capacity), raised, and the hint grows -- never silently truncated.
     OUT_CAP_FACTOR = 3.0
     CAP_HEADROOM = 1.3
+    #: build a tile schedule (rows grouped by neighbour mask) with every rulebook used by a tensor-core layer
+    SCHEDULE_TILES = True
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
                  indice_key=None, subm=False, algo=None, mode='fp32'):
@@ -183,12 +190,17 @@ class _SparseConv(SparseModule):
     def kshape(self):
         return (self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2], self.in_channels, self.out_channels)
 
-    def _rule(self, x):
+    def _rule(self, x, schedule=True):
         key = self.indice_key
         rule = x.indice_dict.get(key) if key is not None else None
         if rule is None:
+            tc = _lib.MODES[self.mode] != _lib.DZ_F32
+            layout = 'row' if tc else 'k'
+            want = self._wants_schedule()
             if self.subm:
-                rule = _RuleSubm(ops.rulebook_subm(x._idx, x._count, x._cap, x.grid_index(), self.kernel_size))
+                sws = ops.new_sched_ws(x._cap, x._idx.device) if want else None
+                t = ops.rulebook_subm(x._idx, x._count, x._cap, x.grid_index(), self.kernel_size, layout=layout, sched_ws=sws)
+                rule = _RuleSubm(None if tc else t, t if tc else None)
             else:
                 in_index = x.grid_index()
                 out_dhw = ops.conv_out_dhw(x.spatial_shape, self.kernel_size, self.stride, self.padding)
@@ -198,11 +210,35 @@ class _SparseConv(SparseModule):
                 hint = getattr(self, '_cap_hint', None)
                 if hint is not None:
                     out_cap = int(min(cells, max(128, (int(hint * self.CAP_HEADROOM) + 127) // 128 * 128)))
-                rule = _RuleConv(*_reorder(ops.rulebook_conv(x._idx, x._count, x._cap, in_index, self.kernel_size,
-                                                              self.stride, self.padding, out_cap)), out_cap)
+                sws = ops.new_sched_ws(out_cap, x._idx.device) if want else None
+                oc, d_n_out, out_index, t, odhw = ops.rulebook_conv(x._idx, x._count, x._cap, in_index, self.kernel_size, self.stride,
+                                                                    self.padding, out_cap, layout=layout, sched_ws=sws)
+                rule = _RuleConv(oc, d_n_out, out_index, (None, t) if tc else (t, None), odhw, out_cap)
+            rule.sched_ws = sws
             if key is not None:
                 x.indice_dict[key] = rule
+        if schedule:
+            self._schedule(rule, x)
         return rule
+
+    def _wants_schedule(self):
+        K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        return self.SCHEDULE_TILES and _lib.MODES[self.mode] != _lib.DZ_F32 and K > 1
+
+    def _schedule(self, rule, x):
+        """tile schedule of a rulebook (once per rulebook; only the tensor-core kernels use it)"""
+        if rule.order is None and rule.sched_ws is not None:
+            rule.order = ops.rulebook_schedule(rule.tab, x._count if self.subm else rule.d_n_out, rule.sched_ws)
+
+    def _table(self, rule):
+        """(table, row_order) for this layer's kernel"""
+        if _lib.MODES[self.mode] != _lib.DZ_F32:
+            if rule.tab is None:                      # rulebook shared with an exact-fp32 layer: convert once
+                rule.tab = ops.table_to_rows(rule.nbr)
+            return rule.tab, rule.order
+        if rule.nbr is None:
+            raise RuntimeError('rulebook %r was built for a tensor-core layer; an exact-fp32 layer cannot share it' % self.indice_key)
+        return rule.nbr, None
 
     def forward_fused(self, x, scale=None, shift=None, residual=None, relu=False):
         rule = self._rule(x)
@@ -210,12 +246,13 @@ class _SparseConv(SparseModule):
         if evs is not None and self.indice_key in evs:               # rulebook was built on the side stream
             torch.cuda.current_stream().wait_event(evs[self.indice_key])
         mode = _lib.MODES[self.mode]
+        nbr, order = self._table(rule)
         if self.subm:
-            out = ops.spconv_fwd(x._feat, rule.nbr, x._count, x._cap, self.packed_weight(mode), scale, shift,
-                                 None if residual is None else residual._feat, relu, mode, kshape=self.kshape)
+            out = ops.spconv_fwd(x._feat, nbr, x._count, x._cap, self.packed_weight(mode), scale, shift,
+                                 None if residual is None else residual._feat, relu, mode, kshape=self.kshape, row_order=order)
             return x._like(out)
-        out = ops.spconv_fwd(x._feat, rule.nbr, rule.d_n_out, rule.out_cap, self.packed_weight(mode), scale, shift, None,
-                             relu, mode, d_n_in=x._count, kshape=self.kshape)
+        out = ops.spconv_fwd(x._feat, nbr, rule.d_n_out, rule.out_cap, self.packed_weight(mode), scale, shift, None,
+                             relu, mode, d_n_in=x._count, kshape=self.kshape, row_order=order)
         t = SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
                              count=rule.d_n_out, n_host=None, index=rule.out_index)
         t._producer = self
@@ -224,11 +261,6 @@ class _SparseConv(SparseModule):
     def forward(self, x):
         shift = None if self.bias is None else self.bias.detach().float()
         return self.forward_fused(x, None, shift, None, False)
-
-
-def _reorder(t):
-    out_coords, d_n_out, out_index, nbr, out_dhw = t
-    return out_coords, d_n_out, out_index, nbr, out_dhw
 
 
 class SubMConv3d(_SparseConv):

@@ -84,28 +84,45 @@ int dz_voxelize_dynamic_mean(const float* points, int n, int c, int B,
                              void* ws, size_t ws_bytes, dz_stream_t stream);
 
 /* ---- rulebook ------------------------------------------------------------------------------------------ */
-/* Neighbour table form of the spconv rulebook: nbr[k*cap + o] = input row feeding output row o through kernel
- * offset k = (kz*KH+ky)*KW+kx, or -1.  The pair set {(k, nbr, o)} equals spconv's indice pairs
- * (SubMConv3d: backbone3d.py:68,93-100,136 ; SparseConv3d: :70-71,169-170,183-184). */
+/* Neighbour-table form of the spconv rulebook.  Two layouts, each optional (NULL = not wanted, at least one given):
+ *   nbr  k-major  (K, cap):  nbr[k*cap + o] = input row feeding output row o through kernel offset
+ *                            k = (kz*KH+ky)*KW+kx, or -1            (exact-fp32 kernel; what the parity tests read)
+ *   tab  row-major (cap, 32): tab[o*32 + k] = the same entry for k < K, -1 up to 26, [27] = bit mask of the live
+ *                            offsets, [28..31] = 0: one 128-byte line per output row   (tensor-core kernels)
+ * The pair set {(k, nbr, o)} equals spconv's indice pairs (SubMConv3d: backbone3d.py:68,93-100,136 ;
+ * SparseConv3d: :70-71,169-170,183-184).
+ * sched_ws (optional, needs tab; dz_rulebook_schedule_ws_bytes(cap) bytes): the kernel also leaves what
+ * dz_rulebook_schedule needs (mask digests, scanned histogram) there. */
 int dz_rulebook_subm(const int32_t* coords, const int* d_n, int cap, int B, int D, int H, int W,
                      const int* ksize3_host, const uint32_t* bitmap, const uint32_t* prefix,
-                     const int32_t* perm, int32_t* nbr, dz_stream_t stream);
-/* Strided conv: generates the output site set (sorted ascending (b,z,y,x)), its grid index and the table.
+                     const int32_t* perm, int32_t* nbr, int32_t* tab, void* sched_ws, dz_stream_t stream);
+/* Strided conv: generates the output site set (sorted ascending (b,z,y,x)), its grid index and the table(s).
  * out_bitmap must be zero on entry. */
 int dz_rulebook_conv(const int32_t* in_coords, const int* d_n_in, int in_cap, int B,
                      const int* in_dhw3_host, const int* ksize3_host, const int* stride3_host,
                      const int* pad3_host, const uint32_t* in_bitmap, const uint32_t* in_prefix,
                      const int32_t* in_perm, int32_t* out_coords, int* d_n_out, int out_cap,
-                     uint32_t* out_bitmap, uint32_t* out_prefix, int32_t* nbr,
-                     void* ws, size_t ws_bytes, dz_stream_t stream);
+                     uint32_t* out_bitmap, uint32_t* out_prefix, int32_t* nbr, int32_t* tab,
+                     void* ws, size_t ws_bytes, void* sched_ws, dz_stream_t stream);
+/* Tile schedule for the tensor-core conv (no reference counterpart; spconv's implicit-GEMM "mask sort" plays the same
+ * role).  order (cap + ceil(cap/128) ints): order[p] = output row at tile position p -- rows with alike neighbour
+ * masks become adjacent, so a 128-row tile skips the kernel offsets none of its rows uses -- and order[cap + j] = the
+ * tile the j-th CTA takes (most live offsets first).  Hand it to dz_spconv_fwd as row_order; results are bit-identical
+ * to the unscheduled call.  sched_ws must be the one the rulebook call filled for this tab. */
+size_t dz_rulebook_schedule_ws_bytes(int cap);
+int dz_rulebook_schedule(const int32_t* tab, int cap, const int* d_n, int32_t* order, void* sched_ws,
+                         size_t ws_bytes, dz_stream_t stream);
 
 /* ---- sparse convolution -------------------------------------------------------------------------------- */
 /* out[o,:] = act( (sum_k in[nbr[k][o],:] @ W[k]) * scale + shift (+ residual[o,:]) )
  * Replaces SubMConv3d/SparseConv3d forward + BatchNorm1d(eval) + bias + residual add + ReLU
  * (backbone3d.py:64-83,105-121).  weight packed (K, cin, cout) f32 (host side repacks spconv's
  * (cout,KD,KH,KW,cin) layout; DZ_TF32 expects (cout, K*cin_pad)).  in_rows = allocated rows of `in`
- * (bounds the TMA gather).  mode: DZ_F32 exact-fp32 FMA, DZ_TF32 tcgen05 tensor cores. */
-int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out,
+ * (bounds the TMA gather).  mode: DZ_F32 exact-fp32 FMA (nbr = k-major table), DZ_TF32 / DZ_TF32X3 tcgen05 tensor
+ * cores (nbr = ROW-major table `tab`, nbr_cap = its rows).
+ * row_order: NULL, or the tile schedule of dz_rulebook_schedule (tensor-core modes only). */
+int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_t* nbr, int K, int nbr_cap,
+                  const int32_t* row_order, const int* d_n_out,
                   int out_cap, const float* weight, const float* scale, const float* shift,
                   const float* residual, int relu, float* out, int cout, int mode, dz_stream_t stream);
 

@@ -141,6 +141,66 @@ def test_spconv_fwd_fp32(cuda, cin, cout):
         assert util.rel_err(out.cpu(), ref) < tol, mode
 
 
+@pytest.mark.parametrize('subm,cin,cout', [(True, 16, 16), (True, 64, 64), (False, 32, 64)])
+def test_tile_schedule_is_a_bit_exact_permutation(cuda, subm, cin, cout):
+    """Row-major table == k-major table; dz_rulebook_schedule: `order` is a permutation of the valid rows grouped by
+    neighbour-mask digest, a 128-row tile then touches fewer kernel offsets than in coordinate order, the tile launch order
+    is heaviest-first, and the scheduled tensor-core conv returns bit-identical features (same per-row accumulation
+    order), incl. rows beyond the count being left alone."""
+    from detzero_b200 import ops
+    from detzero_b200.spconv.pytorch import SparseConvTensor
+    shape, B = [13, 64, 64], 2
+    idx, f = _sparse_input(cuda, 77, B, shape, 0.05, cin)
+    t = SparseConvTensor(f.to(cuda), torch.from_numpy(idx).to(cuda), shape, B)
+    if subm:
+        cap = out_cap = len(idx)
+        sws = ops.new_sched_ws(cap, cuda)
+        (nbr, tab), d_n, n = ops.rulebook_subm(t._idx, t._count, t._cap, t.grid_index(), [3, 3, 3], layout='both', sched_ws=sws), t._count, len(idx)
+    else:
+        cap = out_cap = len(idx) * 2
+        sws = ops.new_sched_ws(cap, cuda)
+        oc, d_n, oi, (nbr, tab), odhw = ops.rulebook_conv(t._idx, t._count, t._cap, t.grid_index(), [3, 3, 3], [2, 2, 2], [1, 1, 1],
+                                                          out_cap=out_cap, layout='both', sched_ws=sws)
+        n = int(d_n.item())
+    k_major = nbr[:, :n].cpu().numpy()
+    assert np.array_equal(tab[:n, :27].cpu().numpy().T, k_major)
+    bits = ((k_major >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    assert np.array_equal(tab[:n, 27].cpu().numpy().astype(np.int64), bits)
+    assert torch.equal(ops.table_to_rows(nbr)[:n], tab[:n])
+    order = ops.rulebook_schedule(tab, d_n, sws)
+    o = order[:n].cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(n))
+    tiles = (cap + 127) // 128
+    to = order[cap:cap + tiles].cpu().numpy()                                # tile launch order: a permutation, heaviest tile first
+    assert np.array_equal(np.sort(to), np.arange(tiles))
+
+    def tile_work(valid):
+        v = np.zeros((27, tiles * 128), bool)
+        v[:, :n] = valid
+        return v.reshape(27, tiles, 128).any(2).sum(0)
+    work = tile_work(k_major[:, o] >= 0)
+    assert np.all(np.diff(work[to]) <= 0)
+    assert work.sum() <= tile_work(k_major >= 0).sum()
+    g = np.random.default_rng(9)
+    w = torch.from_numpy(g.normal(0, 0.2, (cout, 3, 3, 3, cin)).astype(np.float32))
+    scale = torch.from_numpy(g.uniform(0.5, 1.5, cout).astype(np.float32)).to(cuda)
+    shift = torch.from_numpy(g.normal(0, 0.1, cout).astype(np.float32)).to(cuda)
+    res = torch.from_numpy(g.normal(0, 1, (out_cap, cout)).astype(np.float32)).to(cuda)
+    for mode in (_lib.DZ_TF32, _lib.DZ_TF32X3):
+        wp = ops.pack_spconv_weight(w, mode).to(cuda)
+        a = ops.spconv_fwd(t._feat, tab, d_n, out_cap, wp, scale, shift, res, True, mode, kshape=(27, cin, cout),
+                           out=torch.full((out_cap, cout), -7.0, device=cuda))
+        b = ops.spconv_fwd(t._feat, tab, d_n, out_cap, wp, scale, shift, res, True, mode, kshape=(27, cin, cout),
+                           out=torch.full((out_cap, cout), -7.0, device=cuda), row_order=order)
+        c = ops.spconv_fwd(t._feat, nbr, d_n, out_cap, wp, scale, shift, res, True, mode, kshape=(27, cin, cout),
+                           out=torch.full((out_cap, cout), -7.0, device=cuda))      # k-major table converted on the fly
+        assert torch.equal(a, b) and torch.equal(a, c), mode
+        assert torch.all(a[n:] == -7.0)
+    with pytest.raises(RuntimeError):         # the exact-fp32 kernel compacts per offset itself: a schedule is refused loudly
+        ops.spconv_fwd(t._feat, nbr, d_n, out_cap, ops.pack_spconv_weight(w, _lib.DZ_F32).to(cuda), scale, shift, res, True,
+                       _lib.DZ_F32, kshape=(27, cin, cout), row_order=order)
+
+
 @pytest.mark.parametrize('kind,mode,tol', [('VoxelBackBone8x', 'fp32', 2e-5), ('VoxelResBackBone8x', 'fp32', 2e-5),
                                            ('VoxelBackBone8x', 'tf32', 5e-3), ('VoxelResBackBone8x', 'tf32', 5e-3),
                                            ('VoxelBackBone8x', 'tf32x3', 2e-4), ('VoxelResBackBone8x', 'tf32x3', 2e-4)])
