@@ -7,7 +7,8 @@
 A "step" is one pass of the hot path over one batch of synthetic input: raw points -> hard voxelization (+MeanVFE)
 -> rulebooks -> sparse VoxelBackBone8x -> BEV scatter -> BEV backbone -> CenterHead -> decode -> rotated NMS.
 Workload (BASELINE.json configs[1]): CenterPoint 1-sweep, VoxelBackBone8x, synthetic 180 K-pt Waymo-range cloud,
-fp32 storage, batch 1 frame per step per GPU.  Frames shard across ranks with no data-path collective (weak
+fp32 storage, 8 frames per step per GPU by default (the reference's own BATCH_SIZE_PER_GPU, centerpoint_1sweep.yaml:88;
+`--batch 1` gives the single-frame latency configuration).  Frames shard across ranks with no data-path collective (weak
 scaling); see detzero_b200/dist.py for the per-sequence box gather that is NOT part of a step.
 
 Timing: CUDA events around every step on the launching stream, L2 flushed (256 MiB write) between steps outside the
@@ -44,7 +45,8 @@ def parse():
                     help='dense BEV/head convs: tf32 (tcgen05; what the reference gets from cuDNN by default, SURVEY A.6) | fp32 (exact FMA)')
     ap.add_argument('--sp-mode', default=os.environ.get('DZ_SP_MODE', 'tf32'),
                     help='sparse-conv arithmetic: tf32 (tcgen05, 1 pass) | tf32x3 (tcgen05, hi/lo split) | fp32 (exact FMA, spconv default)')
-    ap.add_argument('--batch', type=int, default=1)
+    ap.add_argument('--batch', type=int, default=8,
+                    help='frames per step and GPU; 8 = the reference config (centerpoint_1sweep.yaml:88 BATCH_SIZE_PER_GPU)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-schedule', action='store_true', help='run the tensor-core sparse convs without the mask-grouped tile schedule')
@@ -206,6 +208,7 @@ def main():
         return {'points': pts, 'points_per_frame': b['points_per_frame'], 'frame_id': b['frame_id'], 'batch_size': b['batch_size']}
 
     graph_state = {}
+    e2e_state = {'d2h': 0}
 
     def step_resident(i):
         if graph_state:
@@ -225,8 +228,12 @@ def main():
             else:
                 pts = host_pts[i % NUM_CLOUDS].to(dev, non_blocking=True)
                 pred, _ = model(batch_dict(i, pts))                   # public API: includes the D2H read of counts
-            n = pred[0]['pred_boxes'].shape[0]
-            out_host[0, :n, :7].copy_(pred[0]['pred_boxes'], non_blocking=True)
+            d2h = 0
+            for b, pd in enumerate(pred):                              # every frame's boxes go back to pinned host memory
+                n = pd['pred_boxes'].shape[0]
+                out_host[b, :n, :7].copy_(pd['pred_boxes'], non_blocking=True)
+                d2h += n * 7 * 4
+            e2e_state['d2h'] = d2h + model.last_count_bytes if hasattr(model, 'last_count_bytes') else d2h + 4 * len(pred)
         return pred
 
     def timed(fn, steps, warmup):
@@ -340,7 +347,7 @@ def main():
                    'l2': 'flushed (256 MiB write) between steps, outside the timed intervals',
                    'launch': 'eager' if args.no_graph else 'CUDA graph replay of CenterPoint.forward_device'},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(host_pts[0].numel() * 4),
-                'd2h_bytes_per_step': int(args.batch * 4 + 500 * 7 * 4)},
+                'd2h_bytes_per_step': int(e2e_state['d2h'])},          # boxes of every frame + the count read, last step
         'gpu_launches': launches,
         'clocks': sampler.summary(),
         'roofline': roof,

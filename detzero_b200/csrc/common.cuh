@@ -1,5 +1,6 @@
 // common.cuh -- shared helpers for libdetzero_b200 (sm_100a).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -31,13 +31,18 @@ EncodeTiledFn get_encode_tiled() {
 
 static constexpr int CT_TH = 8, CT_TW = 16, CT_BK = 32;       // pixel patch, channels per k-step group (128 B)
 static constexpr int CT_A_BYTES = CT_TH * CT_TW * CT_BK * 4;  // 16 KB
-static constexpr int CT_THREADS = 192;                        // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
+static constexpr int CT_THREADS = 320;                        // warp0 TMA, warp1 MMA+TMEM, warps 2-5 and 6-9 epilogue (one half of the
+                                                              // accumulator columns each: the epilogue of a single-tile CTA is not overlapped
+                                                              // with anything, so it is spread over 8 warps)
 
-template <int BN, int MT>
+// OCC = CTAs per SM the shared-memory budget is cut for: with many tiles per SM (batched frames) two co-resident
+// single-patch CTAs overlap one CTA's epilogue / set-up with the other's main loop
+template <int BN, int MT, int OCC = 1>
 struct CtCfg {
     static constexpr int B_BYTES = BN * CT_BK * 4;
     static constexpr int STAGE_BYTES = MT * CT_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int BUDGET = OCC == 1 ? 200 * 1024 : 104 * 1024;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = (MT * BN) < 32 ? 32 : MT * BN;      // MT accumulators side by side
 };
@@ -50,11 +55,11 @@ extern "C" int dz_debug_conv2d_trace(long long* host) {
     return cudaMemcpyFromSymbol(host, g_ct_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
 }
 
-template <int BN, int MT>
-__global__ void __launch_bounds__(CT_THREADS, 1)
+template <int BN, int MT, int OCC>
+__global__ void __launch_bounds__(CT_THREADS, OCC)
 k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
               Conv2dParams p, int tiles_x, int tiles_y) {
-    using Cfg = CtCfg<BN, MT>;
+    using Cfg = CtCfg<BN, MT, OCC>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -139,8 +144,11 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc::mbar_wait(tmem_full, 0);
         tc::tcgen05_fence_after();
         if (tr && threadIdx.x == 64) g_ct_trace[3] = clock64();
+        constexpr int COLS = MT * BN, PER = COLS >= 64 ? COLS / 2 : COLS;
+        const int half = (warp - 2) >> 2;
+        if (half == 1 && COLS < 64) { /* nothing left for the second warp group */ } else
 #pragma unroll 1
-        for (int mc = 0; mc < MT * BN; mc += 32) {
+        for (int mc = half * PER; mc < half * PER + PER; mc += 32) {
             const int m = mc / BN, c0 = mc % BN;
             const int y = ty0 + m * CT_TH + row / CT_TW, x = tx0 + row % CT_TW;
             const bool valid = (y < p.Ho) && (x < p.Wo);
@@ -191,24 +199,26 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
     }
     if (p.tma_store && warp >= 2 && lane == 0) tc::tma_store_wait_read();      // the stores must have read the staging buffers
+    if (tr && threadIdx.x == 64) g_ct_trace[5] = clock64();
     tc::tcgen05_fence_before();
     __syncthreads();
     if (tr && threadIdx.x == 0) g_ct_trace[4] = clock64();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int OCC = 1>
 static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t st) {
-    using Cfg = CtCfg<BN, MT>;
+    using Cfg = CtCfg<BN, MT, OCC>;
     static bool configured = false;
     if (!configured) {
-        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32<BN, MT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
     int tiles_x = dz_cdiv(p.Wo, CT_TW), tiles_y = dz_cdiv(p.Ho, CT_TH * MT);
     dim3 grid(tiles_x * tiles_y * p.B, dz_cdiv(p.cout, BN));
     static_assert((MT * BN / 32) * CT_A_BYTES <= Cfg::STAGES * Cfg::STAGE_BYTES || MT * BN < 32, "epilogue staging must fit in the pipeline buffers");
-    k_conv2d_tf32<BN, MT><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmO, p, tiles_x, tiles_y);
+    // (programmatic dependent launch was tried for this kernel and the sparse conv: no measurable gain in the graph replay)
+    k_conv2d_tf32<BN, MT, OCC><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmO, p, tiles_x, tiles_y);
     DZ_LAUNCH_CHECK();
     return DZ_OK;
 }
@@ -263,6 +273,11 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
     // for 256 output pixels)
     const long long tiles1 = (long long)dz_cdiv(p.Wo, CT_TW) * dz_cdiv(p.Ho, CT_TH) * p.B * dz_cdiv(p.cout, bn);
     const bool two = tiles1 >= 2 * DZ_NUM_SMS - 16;
+    // >= 4 tiles per SM (batched frames): two co-resident single-patch CTAs per SM instead of one double-patch CTA, so that one
+    // CTA's epilogue and set-up overlap the other's main loop (batch 8: +2.5 % frames/s).  DZ_CONV2D_OCC2=0 switches it off.
+    static const int occ2 = getenv("DZ_CONV2D_OCC2") ? atoi(getenv("DZ_CONV2D_OCC2")) : 4;
+    if (occ2 && tiles1 >= occ2 * DZ_NUM_SMS && bn == 128) return launch_tf32<128, 1, 2>(p, tmA, tmB, tmO, st);
+    if (occ2 && tiles1 >= occ2 * DZ_NUM_SMS && bn == 64) return launch_tf32<64, 1, 2>(p, tmA, tmB, tmO, st);
     switch (bn) {
         case 128: return two ? launch_tf32<128, 2>(p, tmA, tmB, tmO, st) : launch_tf32<128, 1>(p, tmA, tmB, tmO, st);
         case 64: return two ? launch_tf32<64, 2>(p, tmA, tmB, tmO, st) : launch_tf32<64, 1>(p, tmA, tmB, tmO, st);

@@ -13,7 +13,8 @@ if os.environ.get('DZ_NO_SCHEDULE'):
     from detzero_b200.spconv import pytorch as _sp
     _sp._SparseConv.SCHEDULE_TILES = False
 dev = torch.device('cuda', 0)
-ds, batches = bench.build_inputs(1)
+BATCH = int(os.environ.get('DZ_BATCH', '8'))
+ds, batches = bench.build_inputs(BATCH)
 model = build_network(bench.make_model_cfg('VoxelBackBone8x', 'tf32', sp_mode), 3, ds).eval()
 weights.load_seeded(model, 3)
 model = model.to(dev)
