@@ -368,33 +368,37 @@ extern "C" int dz_boxes_iou_bev(const float* boxes_a, int na, const float* boxes
     return DZ_OK;
 }
 
-// suppression mask: mask[b][i][cb] bit jj set iff j = cb*64+jj > i and IoU(i,j) > thresh
-__global__ void __launch_bounds__(64) k_nms_mask(const float* __restrict__ boxes, const int* __restrict__ d_n, int cap, float thresh,
+// suppression mask: mask[b][i][cb] bit jj set iff j = cb*64+jj > i and IoU(i,j) > thresh.
+// One warp per row box, a lane per column box (two columns each): the rotated-IoU polygon clipping is ~2-3 K cycles per
+// pair, so the pairs are spread over cap/8 x col_blocks CTAs instead of 64 pairs per thread.
+__global__ void __launch_bounds__(256) k_nms_mask(const float* __restrict__ boxes, const int* __restrict__ d_n, int cap, float thresh,
                                                  unsigned long long* __restrict__ mask) {
-    const int b = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+    const int b = blockIdx.z, cb = blockIdx.x;
     const int n = min(d_n[b], cap);
     const int col_blocks = (cap + 63) / 64;
-    if (cb < rb || rb * 64 >= n) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.y * 8, i = row0 + warp;
+    const int rb = row0 >> 6;                        // the CTA's 8 rows lie in one 64-block
+    if (cb < rb || row0 >= n) return;                // CTA-uniform
     __shared__ float cbox[64 * 7];
     const float* fb = boxes + (size_t)b * cap * 7;
-    int cols = min(64, n - cb * 64);
+    const int cols = min(64, n - cb * 64);
     if (cols <= 0) {
-        int i = rb * 64 + threadIdx.x;
-        if (i < n) mask[((size_t)b * cap + i) * col_blocks + cb] = 0ull;
+        if (i < n && lane == 0) mask[((size_t)b * cap + i) * col_blocks + cb] = 0ull;
         return;
     }
-    for (int t = threadIdx.x; t < cols * 7; t += 64) cbox[t] = fb[(size_t)cb * 64 * 7 + t];
+    for (int t = threadIdx.x; t < cols * 7; t += blockDim.x) cbox[t] = fb[(size_t)cb * 64 * 7 + t];
     __syncthreads();
-    int i = rb * 64 + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n) return;                              // warp-uniform
     float me[7];
 #pragma unroll
-    for (int d = 0; d < 7; ++d) me[d] = fb[(size_t)i * 7 + d];
-    unsigned long long bits = 0ull;
-    int start = (rb == cb) ? threadIdx.x + 1 : 0;
-    for (int j = start; j < cols; ++j)
-        if (bev_iou(me, cbox + j * 7) > thresh) bits |= 1ull << j;
-    mask[((size_t)b * cap + i) * col_blocks + cb] = bits;
+    for (int d = 0; d < 7; ++d) me[d] = __ldg(fb + (size_t)i * 7 + d);
+    const bool v0 = lane < cols && cb * 64 + lane > i;
+    const bool v1 = lane + 32 < cols && cb * 64 + lane + 32 > i;
+    const bool h0 = v0 && bev_iou(me, cbox + lane * 7) > thresh;
+    const bool h1 = v1 && bev_iou(me, cbox + (lane + 32) * 7) > thresh;
+    const unsigned lo = __ballot_sync(0xffffffffu, h0), hi = __ballot_sync(0xffffffffu, h1);
+    if (lane == 0) mask[((size_t)b * cap + i) * col_blocks + cb] = (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
 
 // serial keep scan on the device + output assembly
@@ -414,15 +418,30 @@ __global__ void __launch_bounds__(256) k_nms_scan(const float* __restrict__ boxe
     }
     __syncthreads();
     if (threadIdx.x < 32) {
-        // lane l owns removed-word l (col_blocks <= 32)
+        // lane l owns removed-word l (col_blocks <= 32).  Per 64-box block: resolve the suppression inside the block on its
+        // diagonal word (64 dependent steps on registers + one shared-memory read each), then OR the rows of the boxes that
+        // were kept into every lane's word -- instead of one shuffle + dependent read per box over all n boxes.
         unsigned long long remv = 0ull;
         int nk = 0;
-        for (int i = 0; i < n; ++i) {
-            unsigned long long wsel = __shfl_sync(0xffffffffu, remv, i >> 6);
-            if (!((wsel >> (i & 63)) & 1ull)) {
-                if (threadIdx.x == 0) keep[nk] = i;
+        const int lane = threadIdx.x;
+        for (int blk = 0; blk * 64 < n; ++blk) {
+            unsigned long long word = __shfl_sync(0xffffffffu, remv, blk);      // suppressed so far inside this block
+            unsigned long long kept = 0ull;
+            const int cnt = min(64, n - blk * 64);
+            for (int t = 0; t < cnt; ++t) {
+                if (!((word >> t) & 1ull)) {
+                    kept |= 1ull << t;
+                    word |= smask[(size_t)(blk * 64 + t) * col_blocks + blk];
+                }
+            }
+            // every lane computed the same `kept`; record the kept boxes and fold their rows into the removed words
+            unsigned long long kk = kept;
+            while (kk) {
+                const int t = __ffsll((long long)kk) - 1;
+                kk &= kk - 1;
+                if (lane == 0) keep[nk] = blk * 64 + t;
                 ++nk;
-                if (threadIdx.x < col_blocks) remv |= smask[(size_t)i * col_blocks + threadIdx.x];
+                if (lane < col_blocks && lane > blk) remv |= smask[(size_t)(blk * 64 + t) * col_blocks + lane];
             }
         }
         if (threadIdx.x == 0) n_keep = nk;
@@ -455,8 +474,8 @@ extern "C" int dz_nms_bev(const float* boxes, const float* scores, const int32_t
     cudaStream_t st = (cudaStream_t)stream;
     int col_blocks = (cap + 63) / 64;
     unsigned long long* mask = (unsigned long long*)ws;
-    dim3 grid(col_blocks, col_blocks, B);
-    k_nms_mask<<<grid, 64, 0, st>>>(boxes, d_n, cap, thresh, mask);
+    dim3 grid(col_blocks, dz_cdiv(cap, 8), B);
+    k_nms_mask<<<grid, 256, 0, st>>>(boxes, d_n, cap, thresh, mask);
     size_t smem = (size_t)cap * col_blocks * 8 + (size_t)cap * 4;
     static bool configured = false;
     if (!configured) {

@@ -24,8 +24,8 @@ template <int COUT, int PW>
 struct StCfg {
     static constexpr int W_BYTES = COUT * 128;
     static constexpr int STAGE_BYTES = ST_A_BYTES + W_BYTES;
-    // 2 CTAs/SM for COUT <= 64 (the other CTA's prologue/epilogue overlaps this one's main loop), 1 CTA/SM for 128
-    static constexpr int STAGES = COUT >= 128 ? 6 : 4;
+    // 2 CTAs/SM (the other CTA's prologue/epilogue overlaps this one's main loop)
+    static constexpr int STAGES = COUT >= 128 ? 3 : 4;   // Cout = 128 only occurs with K = 3 (conv_out): few k-steps, so 2 CTAs/SM beat depth
     // PW producer warps per stage: warp w gathers its 128/PW rows of the steps it = s, s+STAGES, ... into stage s = w % STAGES
     // (a single warp sustains only one LDGSTS per ~70-130 cycles, tools/ubench_gather.cu; the SM's LSU takes one per ~8.5);
     // warp STAGES*PW issues the MMAs and owns TMEM; warps 0-3 double as the epilogue

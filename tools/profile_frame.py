@@ -17,6 +17,7 @@ BATCH = int(os.environ.get('DZ_BATCH', '8'))
 ds, batches = bench.build_inputs(BATCH)
 model = build_network(bench.make_model_cfg('VoxelBackBone8x', 'tf32', sp_mode), 3, ds).eval()
 weights.load_seeded(model, 3)
+bench.tune_head_for_bench(model)
 model = model.to(dev)
 pts = [torch.from_numpy(b['points']).to(dev) for b in batches]
 
