@@ -336,14 +336,30 @@ __global__ void __launch_bounds__(256) k_sched_scatter(const int32_t* __restrict
     __threadfence();
     const int tiles = (cap + 127) >> 7;
     int32_t* tile_order = order + cap;
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(bins + (27 - __popc(__ldcg(tile_mask + t))), 1);
+    // warp-aggregated (28 bins, thousands of tiles: per-tile shared-memory atomics on the same few counters serialise)
+    const int lane = threadIdx.x & 31;
+    for (int t0 = threadIdx.x - lane; t0 < tiles; t0 += blockDim.x) {
+        const int t = t0 + lane;
+        const int bin = t < tiles ? 27 - __popc(__ldcg(tile_mask + t)) : 99;
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (t < tiles && lane == __ffs(peers) - 1) atomicAdd(bins + bin, __popc(peers));
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
         for (int b = 0; b < 28; ++b) { int c = bins[b]; bins[b] = run; run += c; }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) tile_order[atomicAdd(bins + (27 - __popc(__ldcg(tile_mask + t))), 1)] = t;
+    for (int t0 = threadIdx.x - lane; t0 < tiles; t0 += blockDim.x) {
+        const int t = t0 + lane;
+        const int bin = t < tiles ? 27 - __popc(__ldcg(tile_mask + t)) : 99;
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        const int leader = __ffs(peers) - 1;
+        int start = 0;
+        if (t < tiles && lane == leader) start = atomicAdd(bins + bin, __popc(peers));
+        start = __shfl_sync(0xffffffffu, start, leader);
+        if (t < tiles) tile_order[start + __popc(peers & ((1u << lane) - 1u))] = t;
+    }
 }
 
 extern "C" int dz_rulebook_schedule(const int32_t* tab, int cap, const int* d_n, int32_t* order, void* sched_ws, size_t ws_bytes,

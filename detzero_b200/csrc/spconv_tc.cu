@@ -4,14 +4,17 @@
 // + ReLU, backbone3d.py:64-83,105-121) for DZ_TF32.  spconv's own default keeps TF32 off, so this mode
 // is opt-in (COMPUTE_MODE: tf32) with a stated 2e-3 tolerance.
 //
-// Design: output-stationary implicit GEMM.  A CTA owns 128 consecutive output rows; the reduction dimension is the
-// concatenation (kernel offset k, input channel c) of length K*Cin, cut into 32-float (128-byte) blocks -- for
-// Cin = 16 one block spans two offsets, for Cin = 64 an offset spans two blocks -- so narrow layers still fill the
-// MMA K dimension.  Per block, 4 producer warps gather the neighbour rows straight from global/L2 into shared memory
-// with cp.async (zero-fill for missing neighbours) in the canonical K-major 128B-swizzled UMMA layout, one thread
-// TMA-loads the matching W[cout][k-block] tile, and one thread issues tcgen05.mma (M=128, N=Cout, K=8) into TMEM.
-// Blocks whose offsets have no neighbour anywhere in the tile are skipped.  The producers then become the epilogue:
-// tcgen05.ld -> scale/shift (+residual) -> ReLU -> 128-bit stores.  No atomics: deterministic.
+// Design: output-stationary implicit GEMM.  A CTA owns 128 output rows -- the rows order[p] of one tile of the rulebook's
+// tile schedule (rows with alike neighbour masks, csrc/rulebook.cu), tiles taken heaviest-first -- and reads their
+// neighbour lists from the row-major table (one 128-byte line per row).  The reduction dimension is the concatenation
+// (kernel offset k, input channel c) of length K*Cin, cut into 32-float (128-byte) blocks -- for Cin = 16 one block spans
+// two offsets, for Cin = 64 an offset spans two blocks -- so narrow layers still fill the MMA K dimension.  Blocks whose
+// offsets no row of the tile uses are skipped (that is what the schedule maximises).  Per block, the producer warps (PW
+// per pipeline stage) gather the neighbour rows straight from global/L2 into shared memory with cp.async (zero-fill for
+// missing neighbours) in the canonical K-major 128B-swizzled UMMA layout, one thread TMA-loads the matching
+// W[cout][k-block] tile, and one thread issues tcgen05.mma (M=128, N=Cout, K=8) into TMEM.  Warps 0-3 then run the
+// epilogue: tcgen05.ld -> scale/shift (+residual) -> ReLU -> 128-bit stores to row order[p].  No atomics: deterministic,
+// and bit-identical with or without a schedule (a row's accumulation order over k never changes).
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc.cuh"
@@ -25,7 +28,9 @@ struct StCfg {
     static constexpr int W_BYTES = COUT * 128;
     static constexpr int STAGE_BYTES = ST_A_BYTES + W_BYTES;
     // 2 CTAs/SM (the other CTA's prologue/epilogue overlaps this one's main loop)
-    static constexpr int STAGES = COUT >= 128 ? 3 : 4;   // Cout = 128 only occurs with K = 3 (conv_out): few k-steps, so 2 CTAs/SM beat depth
+    // Cout = 128 only occurs with K = 3 (conv_out): few k-steps, so 2 CTAs/SM beat depth.  (3 stages / 3 CTAs per SM for
+    // Cout <= 32 was measured: no gain.)
+    static constexpr int STAGES = COUT >= 128 ? 3 : 4;
     // PW producer warps per stage: warp w gathers its 128/PW rows of the steps it = s, s+STAGES, ... into stage s = w % STAGES
     // (a single warp sustains only one LDGSTS per ~70-130 cycles, tools/ubench_gather.cu; the SM's LSU takes one per ~8.5);
     // warp STAGES*PW issues the MMAs and owns TMEM; warps 0-3 double as the epilogue
