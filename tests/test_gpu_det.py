@@ -456,3 +456,65 @@ def test_centerpoint_end_to_end_tf32(cuda):
         gb = torch.cat([b['pred_boxes'][:, :3], b['pred_boxes'][:, 6:7], b['pred_scores'][:, None] * 2.5, b['pred_labels'][:, None].float()], 1)
         d = (ga[:, None, :] - gb[None, :, :]).abs().max(dim=2)[0].min(dim=1)[0]
         assert (d < 0.05).float().mean().item() >= 0.9
+
+
+def test_tile_schedule_edge_cases(cuda):
+    """empty level (count 0), a level smaller than one tile, and the K = 3 (3,1,1)/(2,1,1) rulebook of conv_out: the schedule
+    stays a permutation, and scheduled == unscheduled bit for bit (nothing written for a count of 0)"""
+    from detzero_b200 import ops
+    from detzero_b200.spconv.pytorch import SparseConvTensor
+    shape, B = [9, 24, 24], 1
+    idx, f = _sparse_input(cuda, 5, B, shape, 0.06, 64)
+    t = SparseConvTensor(f.to(cuda), torch.from_numpy(idx).to(cuda), shape, B)
+    cap = len(idx)
+    g = np.random.default_rng(3)
+    w27 = ops.pack_spconv_weight(torch.from_numpy(g.normal(0, 0.2, (64, 3, 3, 3, 64)).astype(np.float32)), _lib.DZ_TF32).to(cuda)
+    for n_fake in (0, 5):
+        d_n = torch.tensor([n_fake], dtype=torch.int32, device=cuda)
+        sws = ops.new_sched_ws(cap, cuda)
+        tab = ops.rulebook_subm(t._idx, d_n, cap, t.grid_index(), [3, 3, 3], layout='row', sched_ws=sws)
+        order = ops.rulebook_schedule(tab, d_n, sws)
+        assert np.array_equal(np.sort(order[:n_fake].cpu().numpy()), np.arange(n_fake))
+        tiles = (cap + 127) // 128
+        assert np.array_equal(np.sort(order[cap:cap + tiles].cpu().numpy()), np.arange(tiles))
+        a = ops.spconv_fwd(t._feat, tab, d_n, cap, w27, None, None, None, True, _lib.DZ_TF32, kshape=(27, 64, 64),
+                           out=torch.full((cap, 64), -7.0, device=cuda))
+        b = ops.spconv_fwd(t._feat, tab, d_n, cap, w27, None, None, None, True, _lib.DZ_TF32, kshape=(27, 64, 64),
+                           out=torch.full((cap, 64), -7.0, device=cuda), row_order=order)
+        assert torch.equal(a, b) and torch.all(a[n_fake:] == -7.0)
+    # conv_out geometry: kernel (3,1,1), stride (2,1,1), no padding -> K = 3
+    out_cap = 2 * cap
+    sws = ops.new_sched_ws(out_cap, cuda)
+    oc, d_n, oi, (nbr, tab), odhw = ops.rulebook_conv(t._idx, t._count, t._cap, t.grid_index(), [3, 1, 1], [2, 1, 1], [0, 0, 0],
+                                                      out_cap=out_cap, layout='both', sched_ws=sws)
+    n = int(d_n.item())
+    assert 0 < n <= out_cap
+    assert np.array_equal(tab[:n, :3].cpu().numpy().T, nbr[:, :n].cpu().numpy()) and torch.all(tab[:n, 3:27] == -1)
+    order = ops.rulebook_schedule(tab, d_n, sws)
+    assert np.array_equal(np.sort(order[:n].cpu().numpy()), np.arange(n))
+    w3 = ops.pack_spconv_weight(torch.from_numpy(g.normal(0, 0.2, (128, 3, 1, 1, 64)).astype(np.float32)), _lib.DZ_TF32).to(cuda)
+    a = ops.spconv_fwd(t._feat, tab, d_n, out_cap, w3, None, None, None, True, _lib.DZ_TF32, kshape=(3, 64, 128))
+    b = ops.spconv_fwd(t._feat, tab, d_n, out_cap, w3, None, None, None, True, _lib.DZ_TF32, kshape=(3, 64, 128), row_order=order)
+    assert torch.equal(a[:n], b[:n])
+
+
+def test_batched_frames_equal_single_frames(cuda):
+    """a batch of two frames through the default tensor-core detector gives, frame by frame, exactly the detections of the two
+    single-frame runs (tiles mix rows of both frames, but every row's arithmetic is unchanged)"""
+    from detzero_b200.det import build_network, load_data_to_gpu
+    from detzero_b200.det.dataset import SyntheticWaymoDataset, default_waymo_1sweep_cfg
+    dcfg = default_waymo_1sweep_cfg()
+    dcfg.POINT_CLOUD_RANGE = util.SMALL_RANGE
+    ds = SyntheticWaymoDataset(dcfg, util.CLASS_NAMES, training=False, num_frames=2, n_points=30000)
+    model = build_network(util.model_cfg('VoxelBackBone8x', 'tf32'), 3, ds).eval()
+    weights.load_seeded(model, 21)
+    model = model.to(cuda)
+    clouds = [util.clustered_cloud(30000, 61, c=6), util.clustered_cloud(22000, 62, c=6)]
+    items = [ds.data_processor.forward(ds.point_feature_encoder.forward({'points': p.copy(), 'frame_id': str(k)})) for k, p in enumerate(clouds)]
+    with torch.no_grad():
+        both = model(load_data_to_gpu(ds.collate_batch(items), cuda))[0]
+        singles = [model(load_data_to_gpu(ds.collate_batch([it]), cuda))[0][0] for it in items]
+    assert sum(s['pred_boxes'].shape[0] for s in singles) > 0
+    for k in range(2):
+        for key in ('pred_boxes', 'pred_scores', 'pred_labels'):
+            assert torch.equal(both[k][key], singles[k][key]), (k, key)
