@@ -28,6 +28,9 @@ _SIGS = {
     'dz_voxelize_hard_ws_bytes': (sz, [ci, ci, ci, ci, ci, ci]),
     'dz_voxelize_hard': (ci, [vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp,
                               ci, ci, ci, ci, vp, vp, vp, vp, sz, vp]),
+    'dz_voxelize_hard_batch_ws_bytes': (sz, [ci, ci, ci, ci, ci, ci, ci]),
+    'dz_voxelize_hard_batch': (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, vp, vp, vp, vp, ci, vp,
+                                    ci, ci, ci, vp, vp, vp, vp, sz, vp]),
     'dz_mean_vfe': (ci, [vp, vp, ci, ci, ci, vp, vp]),
     'dz_voxelize_dynamic_ws_bytes': (sz, [ci, ci, ci, ci, ci, ci]),
     'dz_voxelize_dynamic_mean': (ci, [vp, ci, ci, ci, vp, vp, vp, vp, vp, ci, vp, vp, sz, vp]),

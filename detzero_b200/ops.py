@@ -113,6 +113,26 @@ def voxelize_hard(points, xyz_off, c, pc_range, voxel_size, grid_zyx, max_pts, m
     _count(11)
 
 
+def voxelize_hard_batch(clouds, xyz_off, c, pc_range, voxel_size, grid_zyx, max_pts, max_voxels, voxels, coords, num, mean, counters, index):
+    """all frames of a batch in one call (internal streams overlap the frames); see dz_voxelize_hard_batch"""
+    _need_cuda(voxels, *clouds)
+    B = len(clouds)
+    stride = clouds[0].shape[1]
+    for p in clouds:
+        _f32c(p)
+        assert p.shape[1] == stride
+    n_max = max(int(p.shape[0]) for p in clouds)
+    nbytes = lib().dz_voxelize_hard_batch_ws_bytes(n_max, B, max_pts, max_voxels, *index.dhw)
+    ws = workspace(nbytes, voxels.device, 'voxelize_batch')
+    ptrs = (ctypes.c_void_p * B)(*[p.data_ptr() if p.shape[0] else None for p in clouds])
+    ns = (ctypes.c_int * B)(*[int(p.shape[0]) for p in clouds])
+    check(lib().dz_voxelize_hard_batch(ptrs, ns, B, stride, xyz_off, c, farr(pc_range), farr(voxel_size), iarr(grid_zyx), max_pts, max_voxels,
+                                       _p(voxels), _p(coords), _p(num), _p(mean), voxels.shape[0], _p(counters), *index.dhw,
+                                       _p(index.bitmap), _p(index.prefix), _p(index.perm), _p(ws), ws.numel(), _stream()),
+          'voxelize_hard_batch')
+    _count(13 * B)
+
+
 def mean_vfe(voxels, num_i32):
     _need_cuda(voxels, num_i32)
     m, p, c = voxels.shape

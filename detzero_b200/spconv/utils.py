@@ -26,6 +26,9 @@ class Point2VoxelGPU3d:
         self.sparse_shape = [self.grid_zyx[0] + 1, self.grid_zyx[1], self.grid_zyx[2]]     # backbone3d.py:133
         self.device = torch.device(device)
 
+    #: B > 1: one dz_voxelize_hard_batch call (frames overlapped on internal streams) instead of B sequential calls
+    BATCHED = True
+
     def voxelize_batch(self, clouds, xyz_off=0):
         """clouds: list of (n_i, stride) float32 CUDA tensors (one per frame).  Returns capacity-sized tensors and
         device counters -- no host sync.  dict(voxels, coords[b,z,y,x], num, mean, counters, index, cap)"""
@@ -42,9 +45,13 @@ class Point2VoxelGPU3d:
         mean = torch.empty((cap, self.c), dtype=torch.float32, device=dev)
         counters = torch.zeros(3, dtype=torch.int32, device=dev)
         index = ops.GridIndex(B, self.sparse_shape, dev, with_perm_cap=sum(int(c.shape[0]) for c in clouds) + 1)
-        for b, pts in enumerate(clouds):
-            ops.voxelize_hard(pts, xyz_off, self.c, self.range, self.vsize, self.grid_zyx, self.max_pts,
-                              self.max_voxels, b, voxels, coords, num, mean, counters, index)
+        if B > 1 and self.BATCHED:
+            ops.voxelize_hard_batch(clouds, xyz_off, self.c, self.range, self.vsize, self.grid_zyx, self.max_pts, self.max_voxels,
+                                    voxels, coords, num, mean, counters, index)
+        else:
+            for b, pts in enumerate(clouds):
+                ops.voxelize_hard(pts, xyz_off, self.c, self.range, self.vsize, self.grid_zyx, self.max_pts,
+                                  self.max_voxels, b, voxels, coords, num, mean, counters, index)
         return dict(voxels=voxels, coords=coords, num=num, mean=mean, counters=counters, index=index, cap=cap)
 
     def note_count(self, wanted, cap):

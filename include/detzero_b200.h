@@ -68,6 +68,16 @@ int dz_voxelize_hard(const float* points, int n, int point_stride, int xyz_off, 
                      int B, int iD, int iH, int iW, uint32_t* index_bitmap, uint32_t* index_prefix,
                      int32_t* index_perm,
                      void* ws, size_t ws_bytes, dz_stream_t stream);
+/* The same for the B frames of a batch in ONE call (frames = batch indices 0..B-1, d_counters zero or carried on entry):
+ * the frames run on internal streams forked from / joined to `stream` and only wait for each other's running totals, so
+ * their latency-bound kernels overlap.  points_host / n_host are HOST arrays of device pointers / point counts.
+ * Identical results to B calls of dz_voxelize_hard in frame order. */
+size_t dz_voxelize_hard_batch_ws_bytes(int n_max, int B, int max_pts, int max_voxels, int iD, int iH, int iW);
+int dz_voxelize_hard_batch(const float* const* points_host, const int* n_host, int B, int point_stride, int xyz_off, int c,
+                           const float* range6_host, const float* vsize3_host, const int* grid_zyx3_host, int max_pts,
+                           int max_voxels, float* voxels, int32_t* coords, int32_t* num_per_voxel, float* mean, int cap,
+                           int* d_counters, int iD, int iH, int iW, uint32_t* index_bitmap, uint32_t* index_prefix,
+                           int32_t* index_perm, void* ws, size_t ws_bytes, dz_stream_t stream);
 
 /* MeanVFE.forward (vfe.py:66-83) on an already voxelized batch: out (M,C) = voxels.sum(1) / max(num,1) */
 int dz_mean_vfe(const float* voxels, const int32_t* num_per_voxel, int M, int P, int C, float* out,
