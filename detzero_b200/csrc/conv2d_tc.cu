@@ -273,9 +273,10 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
     // for 256 output pixels)
     const long long tiles1 = (long long)dz_cdiv(p.Wo, CT_TW) * dz_cdiv(p.Ho, CT_TH) * p.B * dz_cdiv(p.cout, bn);
     const bool two = tiles1 >= 2 * DZ_NUM_SMS - 16;
-    // >= 4 tiles per SM (batched frames): two co-resident single-patch CTAs per SM instead of one double-patch CTA, so that one
-    // CTA's epilogue and set-up overlap the other's main loop (batch 8: +2.5 % frames/s).  DZ_CONV2D_OCC2=0 switches it off.
-    static const int occ2 = getenv("DZ_CONV2D_OCC2") ? atoi(getenv("DZ_CONV2D_OCC2")) : 4;
+    // >= 1 single-patch tile per SM: two co-resident single-patch CTAs per SM instead of one double-patch CTA, so that one
+    // CTA's epilogue and set-up overlap the other's main loop (batch 8: +2.5 % frames/s, batch 1: +1.9 %).
+    // DZ_CONV2D_OCC2=0 switches it off, =n sets the threshold to n tiles per SM.
+    static const int occ2 = getenv("DZ_CONV2D_OCC2") ? atoi(getenv("DZ_CONV2D_OCC2")) : 1;
     if (occ2 && tiles1 >= occ2 * DZ_NUM_SMS && bn == 128) return launch_tf32<128, 1, 2>(p, tmA, tmB, tmO, st);
     if (occ2 && tiles1 >= occ2 * DZ_NUM_SMS && bn == 64) return launch_tf32<64, 1, 2>(p, tmA, tmB, tmO, st);
     switch (bn) {
