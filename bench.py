@@ -356,7 +356,8 @@ def main():
     line = {
         'metric': 'Waymo-shape frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'fp32' if args.mode == 'fp32' else 'fp32 storage, %s dense BEV convs' % args.mode,
+        'vs_baseline': None, 'dtype': ('fp32' if args.mode == 'fp32' and args.sp_mode == 'fp32' else
+                                      'fp32 storage and accumulation; products: sparse convs %s, dense BEV/head convs %s' % (args.sp_mode, args.mode)),
         'data': 'synthetic',
         'config': {'workload': 'CenterPoint 1-sweep %s, synthetic 180K-pt Waymo-range cloud, fp32, batch %d/GPU'
                                % (args.backbone, args.batch),
