@@ -237,3 +237,37 @@ def test_yaml_config_builds_registry_model():
     names = [type(m).__name__ for m in model.module_list]
     assert names == ['MeanVFE', 'VoxelResBackBone8x', 'HeightCompression', 'BaseBEVBackbone', 'CenterHead']
     assert model.backbone3d.sparse_shape == [41, 1504, 1504] and model.vfe.max_voxels == 200000
+
+
+def test_row_major_table_helper_matches_k_major():
+    """ops.table_to_rows: the host-side conversion between the two rulebook table layouts of include/detzero_b200.h
+    (k-major (K, cap) <-> row-major (cap, 32) with the neighbour bit mask in column 27); pure torch, runs on the CPU"""
+    from detzero_b200 import ops
+    g = np.random.default_rng(4)
+    idx = weights.random_sparse_coords(9, 1, [7, 12, 12], 0.15)
+    pairs = spconv_ref.rulebook_subm(idx, [7, 12, 12], 3)
+    n = len(idx)
+    nbr = torch.full((27, n), -1, dtype=torch.int32)
+    for k, (i_in, i_out) in enumerate(pairs):
+        nbr[k, torch.as_tensor(np.asarray(i_out), dtype=torch.long)] = torch.as_tensor(np.asarray(i_in), dtype=torch.int32)
+    tab = ops.table_to_rows(nbr)
+    assert tab.shape == (n, 32) and torch.equal(tab[:, :27].t().contiguous(), nbr)
+    bits = ((nbr >= 0).to(torch.int64) << torch.arange(27)[:, None]).sum(0)
+    assert torch.equal(tab[:, 27].to(torch.int64), bits) and torch.all(tab[:, 28:] == 0)
+    assert int(bits[0]) & (1 << 13)                      # every site is its own centre-tap neighbour
+
+
+def test_bench_cpu_arm_produces_detections():
+    """the CPU arm of bench.py (`--impl reference` / cpu_baseline) runs the oracle chain on the bench workload with the same
+    head calibration as the GPU arm: a frame must reach post-processing with real work (500 boxes into the rotated NMS)"""
+    import sys
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        import bench
+        torch.set_num_threads(min(8, os.cpu_count() or 1))
+        out = bench.cpu_frame_fn('VoxelBackBone8x')(0)
+    finally:
+        sys.argv = argv
+    d = out[0]
+    assert d['pred_boxes'].shape == (500, 7) and d['pred_scores'].shape == (500,)
+    assert float(d['pred_scores'].max()) > 0.3 and int(d['pred_labels'].min()) >= 1
