@@ -57,8 +57,8 @@ def parse():
 
 
 def make_model_cfg(backbone, mode, sp_mode):
-    from tests import util
-    cfg = util.model_cfg(backbone, mode)
+    from detzero_b200 import synthetic
+    cfg = synthetic.model_cfg(backbone, mode)
     cfg.BACKBONE_3D.COMPUTE_MODE = sp_mode
     if os.environ.get('DZ_NO_OVERLAP'):
         cfg.BACKBONE_3D.OVERLAP_RULEBOOKS = False      # diagnostic: rulebooks inline on the main stream
@@ -81,9 +81,9 @@ def tune_head_for_bench(model):
 
 
 def build_inputs(batch):
+    from detzero_b200 import synthetic
     from detzero_b200.det.dataset import SyntheticWaymoDataset, default_waymo_1sweep_cfg
-    from tests import util
-    ds = SyntheticWaymoDataset(default_waymo_1sweep_cfg(), util.CLASS_NAMES, training=False, num_frames=NUM_CLOUDS * batch,
+    ds = SyntheticWaymoDataset(default_waymo_1sweep_cfg(), synthetic.CLASS_NAMES, training=False, num_frames=NUM_CLOUDS * batch,
                                n_points=N_POINTS)
     batches = []
     for i in range(NUM_CLOUDS):
@@ -189,8 +189,7 @@ def main():
         return run_reference(args)
     import torch
     import torch.distributed as dist
-    from oracle import weights
-    from detzero_b200 import ops
+    from detzero_b200 import ops, synthetic as weights
     from detzero_b200.det import build_network
 
     world = int(os.environ.get('WORLD_SIZE', '1'))

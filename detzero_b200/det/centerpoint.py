@@ -72,10 +72,29 @@ class CenterPoint(nn.Module):
 
     def forward_device(self, batch_dict):
         """all device work of one batch, no host sync (capturable in a CUDA graph); result =
-        batch_dict['final_boxes_padded'] (B,500,9) + ['final_boxes_count'] (B)"""
+        batch_dict['final_boxes_padded'] (B,500,9) + ['final_boxes_count'] (B) + ['overflow_flag'] (1,) int32: number of
+        sparse levels (and the voxelizer) whose true row count exceeded the capacity the kernels clamped to -- nonzero
+        means rows were dropped and the step must be re-run with larger capacities (post_processing raises)"""
         for m in self.module_list:
             batch_dict = m(batch_dict)
+        batch_dict['overflow_flag'] = self._overflow_flag(batch_dict)
         return batch_dict
+
+    @staticmethod
+    def _levels(batch_dict):
+        levels = [t for t in batch_dict.get('multi_scale_3d_features', {}).values()] + [batch_dict.get('encoded_spconv_tensor')]
+        return [t for t in levels if t is not None]
+
+    def _overflow_flag(self, batch_dict):
+        """device-side OR over every capacity-bounded count of the step (every kernel clamps with min(count, cap), so an
+        overflow would otherwise truncate silently under CUDA-graph replay)"""
+        flags = [(t._count > t._cap) for t in CenterPoint._levels(batch_dict)]
+        vw = batch_dict.get('voxel_wanted')
+        if vw is not None:
+            flags.append(vw[0] > vw[1])
+        if not flags:
+            return torch.zeros(1, dtype=torch.int32, device=batch_dict['final_boxes_count'].device)
+        return torch.cat([f.view(1) for f in flags]).sum(dtype=torch.int32).view(1)
 
     def capture_graph(self, batch_dict, warmup=2):
         """Capture forward_device for a fixed input shape in a CUDA graph (streams + graphs instead of a tracing compiler).
@@ -104,18 +123,37 @@ class CenterPoint(nn.Module):
     def post_processing(self, batch_dict):
         """centerpoint.py:210-307 (single-stage branch): pred_dicts = final_box_dicts.  The recall bookkeeping
         (generate_recall_record) needs gt boxes + 3D IoU and only feeds a log line; it is reported as empty.
-        This is the ONE device->host read of the step: box counts + per-level site counts (overflow check)."""
+        This is the ONE device->host read of the step: box counts + the overflow flag + per-level site counts.  Works on
+        the static output of a replayed CUDA graph as well: the counts are re-read on every call (never cached), every
+        capacity hint is raised BEFORE an overflow is reported, and an overflow always raises (never truncates)."""
         counts = batch_dict['final_boxes_count']
-        levels = [t for t in batch_dict.get('multi_scale_3d_features', {}).values()] + \
-                 [batch_dict.get('encoded_spconv_tensor')]
-        levels = [t for t in levels if t is not None and t._n is None]
+        levels = CenterPoint._levels(batch_dict)
         vw = batch_dict.get('voxel_wanted')
-        flat = torch.cat([counts.flatten()] + [t._count for t in levels] + ([vw[0]] if vw is not None else [])).tolist()
+        ovf = batch_dict.get('overflow_flag')
+        parts = [counts.flatten().int()] + ([ovf] if ovf is not None else []) + [t._count for t in levels] + ([vw[0]] if vw is not None else [])
+        flat = torch.cat(parts).tolist()
         nb = counts.numel()
+        pos = nb
+        flagged = 0
+        if ovf is not None:
+            flagged = int(flat[pos]); pos += 1
+        over = []
+        for t in levels:
+            n = int(flat[pos]); pos += 1
+            t._n = None
+            try:
+                t.set_num(n)                               # updates the producing layer's capacity hint, raises on overflow
+            except RuntimeError as e:
+                over.append(str(e))
+                t._n = t._cap
         if vw is not None:
-            vw[2].note_count(int(flat[-1]), vw[1])
-        for t, n in zip(levels, flat[nb:]):
-            t.set_num(int(n))                              # raises on overflow, updates the layer capacity hints
+            try:
+                vw[2].note_count(int(flat[pos]), vw[1])
+            except RuntimeError as e:
+                over.append(str(e))
+        if over or flagged:
+            raise RuntimeError('capacity overflow in %d place(s) (all hints raised; re-run the step, re-capture any CUDA graph): %s'
+                               % (max(len(over), flagged), '; '.join(over) or 'device flag set'))
         shaped = torch.tensor(flat[:nb]).view(counts.shape)
         pred_dicts = dense.CenterHead.boxes_to_dicts(batch_dict['final_boxes_padded'], shaped)
         batch_dict['final_box_dicts'] = pred_dicts

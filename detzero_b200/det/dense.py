@@ -27,18 +27,18 @@ def _nchw_view(x_nhwc):
     return x_nhwc.permute(0, 3, 1, 2)
 
 
-_pack_cache = {}
-
-
 def _cached(key_obj, tensors, fn):
-    ver = tuple((t._version, t.data_ptr()) for t in tensors if t is not None)
-    key = (id(key_obj[0]), key_obj[1]) if isinstance(key_obj, tuple) else id(key_obj)
-    hit = _pack_cache.get(key)
+    """kernel-layout copies are cached ON THE MODULE (a global dict keyed by id() can hand a freed model's weights to a new
+    model that recycles the id and the allocator address)"""
+    mod, sub = key_obj if isinstance(key_obj, tuple) else (key_obj, None)
+    ver = tuple((t._version, t.data_ptr(), t.device) for t in tensors if t is not None)
+    cache = mod.__dict__.setdefault('_dz_pack', {})
+    hit = cache.get(sub)
     if hit is not None and hit[0] == ver:
         return hit[1]
     with torch.no_grad():
         val = fn()
-    _pack_cache[key] = (ver, val)
+    cache[sub] = (ver, val)
     return val
 
 

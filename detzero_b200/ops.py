@@ -246,14 +246,20 @@ def round_tf32(t):
 
 
 def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None,
-               d_n_in=None, kshape=None, row_order=None):
+               d_n_in=None, kshape=None, row_order=None, layout=None):
     """feats (in_cap, cin); weight_packed per pack_spconv_weight; kshape = (K, cin, cout).
     nbr: k-major (K, cap) table for DZ_F32; row-major (cap, 32) table for the tensor-core modes (a k-major table is
-    converted on the fly); row_order: tile schedule from rulebook_schedule (tensor-core modes)"""
+    converted on the fly); layout: 'k' | 'row' says which one `nbr` is (None: inferred from the shape, ambiguous only for
+    cap == K or cap == 32 -- callers that know pass it); row_order: tile schedule from rulebook_schedule (tensor-core modes)"""
     _need_cuda(feats, nbr, weight_packed)
     K, cin, cout = kshape if kshape is not None else weight_packed.shape
-    if mode != _lib.DZ_F32 and not (nbr.shape[1] == 32 and nbr.shape[0] != K):
+    if layout is None:
+        layout = 'row' if (nbr.shape[1] == 32 and nbr.shape[0] != K) else 'k'
+    assert layout in ('k', 'row')
+    if mode != _lib.DZ_F32 and layout == 'k':
         nbr = table_to_rows(nbr)
+    elif mode == _lib.DZ_F32 and layout == 'row':
+        raise RuntimeError('the exact-fp32 kernel needs the k-major (K, cap) table')
     assert feats.shape[1] == cin and (nbr.shape[0] == K if mode == _lib.DZ_F32 else nbr.shape[1] == 32)
     if out is None:
         out = torch.empty((out_cap, cout), dtype=torch.float32, device=feats.device)

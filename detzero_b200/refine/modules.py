@@ -54,21 +54,19 @@ def make_conv_layers(cfg, c_in, c_out, output_use_norm=False):
     return nn.Sequential(*layers)
 
 
-_w_cache = {}
-
-
 def _w2d(m, mode=_lib.DZ_F32):
-    """weight of Linear / Conv1d(k=1) / Conv2d(k=1) as (N, K); rounded to TF32 (RN) once for the tensor-core mode"""
+    """weight of Linear / Conv1d(k=1) / Conv2d(k=1) as (N, K); rounded to TF32 (RN) once for the tensor-core mode.
+    Cached on the module itself (not in a global keyed by id(): ids / addresses are recycled after a model is freed)."""
     w = m.weight
-    key = (id(m), mode)
-    ver = (w._version, w.data_ptr())
-    hit = _w_cache.get(key)
+    ver = (w._version, w.data_ptr(), w.device)
+    cache = m.__dict__.setdefault('_dz_w2d', {})
+    hit = cache.get(mode)
     if hit is not None and hit[0] == ver:
         return hit[1]
     w2 = w.detach().reshape(w.shape[0], -1).contiguous().float()
     if mode == _lib.DZ_TF32:
         w2 = ops.round_tf32(w2)
-    _w_cache[key] = (ver, w2)
+    cache[mode] = (ver, w2)
     return w2
 
 

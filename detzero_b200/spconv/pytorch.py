@@ -112,15 +112,17 @@ class SparseModule(nn.Module):
     pass
 
 
-_fold_cache = {}
+def _tensor_state(ts):
+    """identity + in-place version of every involved tensor (load_state_dict bumps ``_version``; ``.to()`` swaps data_ptr)"""
+    return tuple((t._version, t.data_ptr(), t.device) for t in ts)
 
 
 def fold_bn(bn, conv_bias, device=None):
-    """eval-mode BatchNorm folded to (scale, shift): y = conv*scale + shift.  Cached per module; refreshed when any
-    involved tensor is modified in place (load_state_dict bumps ``_version``)."""
+    """eval-mode BatchNorm folded to (scale, shift): y = conv*scale + shift.  Cached ON THE MODULE (never in a global keyed
+    by id(): ids and allocator addresses are recycled after a model is freed); refreshed when any involved tensor changes."""
     ts = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, conv_bias) if t is not None]
-    ver = tuple((t._version, t.data_ptr()) for t in ts)
-    hit = _fold_cache.get(id(bn))
+    ver = _tensor_state(ts)
+    hit = bn.__dict__.get('_dz_fold')
     if hit is not None and hit[0] == ver:
         return hit[1], hit[2]
     with torch.no_grad():
@@ -133,7 +135,7 @@ def fold_bn(bn, conv_bias, device=None):
         if conv_bias is not None:
             shift = shift + conv_bias.detach().float() * scale
         scale, shift = scale.contiguous(), shift.contiguous()
-    _fold_cache[id(bn)] = (ver, scale, shift)
+    bn.__dict__['_dz_fold'] = (ver, scale, shift)
     return scale, shift
 
 
@@ -205,7 +207,12 @@ class _SparseConv(SparseModule):
                 in_index = x.grid_index()
                 out_dhw = ops.conv_out_dhw(x.spatial_shape, self.kernel_size, self.stride, self.padding)
                 cells = x.batch_size * out_dhw[0] * out_dhw[1] * out_dhw[2]
-                grow = self.OUT_CAP_FACTOR if max(self.stride) > 1 and min(self.kernel_size) > 1 else 1.0
+                # one input site reaches prod_d ceil(k_d / s_d) output sites at most (8 for k3 s2, 2 for conv_out's (3,1,1)/(2,1,1));
+                # in practice k3 s2 grows the site count by <= ~1.8x, hence the smaller first-run factor
+                worst = 1
+                for kd, sd_ in zip(self.kernel_size, self.stride):
+                    worst *= -(-kd // sd_)
+                grow = min(float(worst), self.OUT_CAP_FACTOR)
                 out_cap = int(min(cells, max(64, int(x._cap * grow))))
                 hint = getattr(self, '_cap_hint', None)
                 if hint is not None:
@@ -247,12 +254,13 @@ class _SparseConv(SparseModule):
             torch.cuda.current_stream().wait_event(evs[self.indice_key])
         mode = _lib.MODES[self.mode]
         nbr, order = self._table(rule)
+        lay = 'k' if mode == _lib.DZ_F32 else 'row'
         if self.subm:
             out = ops.spconv_fwd(x._feat, nbr, x._count, x._cap, self.packed_weight(mode), scale, shift,
-                                 None if residual is None else residual._feat, relu, mode, kshape=self.kshape, row_order=order)
+                                 None if residual is None else residual._feat, relu, mode, kshape=self.kshape, row_order=order, layout=lay)
             return x._like(out)
         out = ops.spconv_fwd(x._feat, nbr, rule.d_n_out, rule.out_cap, self.packed_weight(mode), scale, shift, None,
-                             relu, mode, d_n_in=x._count, kshape=self.kshape, row_order=order)
+                             relu, mode, d_n_in=x._count, kshape=self.kshape, row_order=order, layout=lay)
         t = SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
                              count=rule.d_n_out, n_host=None, index=rule.out_index)
         t._producer = self

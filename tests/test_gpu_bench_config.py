@@ -1,0 +1,185 @@
+"""Parity AT THE BENCHMARKED CONFIGURATION (BASELINE configs[1]): 180 K-point synthetic Waymo-range clouds on the full
+1504 x 1504 x 41 lattice through the registry-built CenterPoint, single frame and 8-frame batch, against the CPU oracle
+chain (voxelizer C restatement -> spconv restatement -> torch-CPU BEV/head -> decode -> NMS); CUDA-graph replay == eager
+bit for bit; capacity-overflow detection under replay.  VERDICT r1 "weak #2"."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import det_ref
+from tests import util
+from tests.test_gpu_det import _assert_same_detections
+
+pytestmark = pytest.mark.gpu
+
+N_POINTS = 180000
+POST = dict(MAX_OBJ_PER_SAMPLE=500, SCORE_THRESH=0.03, POST_CENTER_LIMIT_RANGE=[-80, -80, -10.0, 80, 80, 10.0],
+            NMS_THRESH=0.7, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500)
+#: per-level feature bound vs the fp32 oracle, per sparse-conv mode (rel. to the level's max |feature|)
+LEVEL_TOL = {'fp32': 2e-5, 'tf32x3': 2e-4, 'bf16x2': 2e-4, 'tf32': 5e-3, 'bf16': 3e-2}
+#: modes whose detections must equal the oracle's (count, scores 1e-5, boxes 1e-3); the others: >= 90 % within 5 cm
+EXACT_MODES = ('fp32', 'tf32x3', 'bf16x2')
+
+
+def _modes():
+    from detzero_b200 import _lib
+    return [m for m in ('fp32', 'tf32x3', 'bf16x2', 'tf32', 'bf16') if m in _lib.MODES]
+
+
+@pytest.fixture(scope='module')
+def world(cuda):
+    """dataset, 8 collated frames, seeded + bench-calibrated weights, and the oracle chain of every frame (computed once)"""
+    import bench
+    from detzero_b200 import synthetic
+    from detzero_b200.det import build_network
+    ds, batches = bench.build_inputs(1)                 # 4 single-frame batches (seeds 0..3), padded to 180 K points
+    ds8, batches8 = bench.build_inputs(8)               # frames 0..7 in the first batch
+    ref_model = build_network(synthetic.model_cfg('VoxelBackBone8x', 'fp32'), 3, ds).eval()
+    synthetic.load_seeded(ref_model, 3)
+    sd = bench.tune_head_for_bench(ref_model)
+    vox = oracle.Point2VoxelCPU3d(util.VOXEL, util.WAYMO_RANGE, 5, 5, 200000)
+    frames = []
+    pts8 = batches8[0]['points']
+    torch.set_num_threads(16)
+    for b in range(8):
+        pts = pts8[pts8[:, 0] == b][:, 1:]
+        with torch.no_grad():
+            v, c, n = vox.point_to_voxel(pts)
+            lv = det_ref.voxel_backbone(sd, 'backbone3d.', det_ref.mean_vfe(v, n), np.pad(c, ((0, 0), (1, 0))), [41, 1504, 1504], 1, False)
+            s2d = det_ref.bev_backbone(sd, 'backbone2d.', det_ref.height_compression(lv['out']), [5, 5], [1, 2], [1, 2])
+            maps = det_ref.center_head_maps(sd, 'dense_head.', s2d, ['center', 'center_z', 'dim', 'rot', 'iou', 'hm'])
+            boxes = det_ref.generate_predicted_boxes(maps, util.WAYMO_RANGE, util.VOXEL, 8, POST, use_iou=True)[0]
+        frames.append(dict(coords=c, levels=lv, boxes=boxes))
+        if b == 0:
+            assert boxes['pred_boxes'].shape[0] > 100, 'the bench calibration should give a busy post-processing stage'
+    return dict(ds=ds, batches=batches, ds8=ds8, batches8=batches8, sd=sd, frames=frames)
+
+
+def _model(world, mode, cuda, ds_key='ds8', dense_mode=None):
+    import bench
+    from detzero_b200 import synthetic
+    from detzero_b200.det import build_network
+    cfg = synthetic.model_cfg('VoxelBackBone8x', dense_mode or ('fp32' if mode == 'fp32' else 'tf32'))
+    cfg.BACKBONE_3D.COMPUTE_MODE = mode
+    model = build_network(cfg, 3, world[ds_key]).eval()
+    synthetic.load_seeded(model, 3)
+    bench.tune_head_for_bench(model)
+    return model.to(cuda)
+
+
+def _bd(batch, dev):
+    return {'points': torch.from_numpy(batch['points']).to(dev), 'points_per_frame': batch['points_per_frame'],
+            'frame_id': batch['frame_id'], 'batch_size': batch['batch_size']}
+
+
+def _settle(model, bd_fn, tries=6):
+    """run until the capacity hints have settled (an overflow raises, raises the hints, and the step is re-run)"""
+    for _ in range(tries):
+        try:
+            with torch.no_grad():
+                return model(bd_fn())
+        except RuntimeError as e:
+            if 'overflow' not in str(e):
+                raise
+    raise AssertionError('capacities did not settle')
+
+
+def _split_level(t, B):
+    """SparseConvTensor of a batch -> per-frame (indices[:,1:], features)"""
+    idx, f = t.indices.cpu().numpy(), t.features.float().cpu()
+    return [(idx[idx[:, 0] == b][:, 1:], f[torch.from_numpy(idx[:, 0] == b)]) for b in range(B)]
+
+
+def _check_against_oracle(world, mode, batch_dict, pred, frame_ids):
+    B = len(frame_ids)
+    for name in ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out'):
+        t = batch_dict['encoded_spconv_tensor'] if name == 'out' else batch_dict['multi_scale_3d_features'][name]
+        for b, (idx, f) in enumerate(_split_level(t, B)):
+            w = world['frames'][frame_ids[b]]['levels'][name]
+            assert np.array_equal(idx, w.idx[:, 1:]), (mode, name, b)               # same sites, same (sorted) order
+            assert util.rel_err(f, w.f) < LEVEL_TOL[mode], (mode, name, b, util.rel_err(f, w.f))
+    for b in range(B):
+        want = world['frames'][frame_ids[b]]['boxes']
+        if mode in EXACT_MODES:
+            _assert_same_detections(pred[b], want)
+        else:
+            ga, gb = pred[b], want
+            assert abs(ga['pred_boxes'].shape[0] - gb['pred_boxes'].shape[0]) <= max(3, gb['pred_boxes'].shape[0] // 20)
+            a = torch.cat([ga['pred_boxes'][:, :3].cpu(), ga['pred_boxes'][:, 6:7].cpu(), ga['pred_scores'][:, None].cpu() * 2.5,
+                           ga['pred_labels'][:, None].float().cpu()], 1)
+            w = torch.cat([gb['pred_boxes'][:, :3], gb['pred_boxes'][:, 6:7], gb['pred_scores'][:, None] * 2.5, gb['pred_labels'][:, None].float()], 1)
+            d = (w[:, None, :] - a[None, :, :]).abs().max(dim=2)[0].min(dim=1)[0]
+            assert (d < 0.05).float().mean().item() >= 0.9, (mode, b)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'tf32x3', 'bf16x2', 'tf32', 'bf16'])
+def test_full_lattice_single_frame_vs_oracle(cuda, world, mode):
+    if mode not in _modes():
+        pytest.skip('mode %s not built' % mode)
+    model = _model(world, mode, cuda, 'ds')
+    pred, _ = _settle(model, lambda: _bd(world['batches'][0], cuda))
+    with torch.no_grad():
+        bd = model.forward_device(_bd(world['batches'][0], cuda))
+        pred, _ = model.post_processing(bd)
+    _check_against_oracle(world, mode, bd, pred, [0])
+
+
+@pytest.mark.parametrize('mode', ['tf32x3', 'bf16x2', 'tf32', 'bf16'])
+def test_full_lattice_batch8_vs_oracle_and_graph_replay(cuda, world, mode):
+    """the bench step itself: 8 frames per step; eager == oracle, CUDA-graph replay == eager bit for bit on every input
+    batch, the overflow flag is read after every replay"""
+    import bench
+    if mode not in _modes():
+        pytest.skip('mode %s not built' % mode)
+    model = _model(world, mode, cuda)
+    batches = world['batches8']
+    for bt in batches:                                   # settle the capacity hints on every input of the replay loop
+        _settle(model, lambda: _bd(bt, cuda))
+    with torch.no_grad():
+        bd = model.forward_device(_bd(batches[0], cuda))
+        pred, _ = model.post_processing(bd)
+    _check_against_oracle(world, mode, bd, pred, list(range(8)))
+    eager = []
+    with torch.no_grad():
+        for bt in batches:
+            o = model.forward_device(_bd(bt, cuda))
+            model.post_processing(o)
+            eager.append((o['final_boxes_padded'].clone(), o['final_boxes_count'].clone(),
+                          o['encoded_spconv_tensor']._feat.clone(), o['encoded_spconv_tensor']._count.clone()))
+    static = _bd(batches[0], cuda)
+    g, out = model.capture_graph(static, warmup=1)
+    for rep in range(2):
+        for i, bt in enumerate(batches):
+            static['points'].copy_(torch.from_numpy(bt['points']))
+            g.replay()
+            model.post_processing(out)                    # raises if any level overflowed in THIS replay
+            n = int(out['encoded_spconv_tensor']._count.item())
+            assert torch.equal(out['final_boxes_count'], eager[i][1]), (mode, i)
+            assert torch.equal(out['final_boxes_padded'], eager[i][0]), (mode, i)
+            assert n == int(eager[i][3].item()) and torch.equal(out['encoded_spconv_tensor']._feat[:n], eager[i][2][:n]), (mode, i)
+
+
+def test_overflow_is_detected_under_graph_replay(cuda, world):
+    """capacities frozen from a SPARSE frame, then a dense frame replayed through the graph: the device flag must raise
+    (never a silent truncation), every hint must have grown, and the re-run must succeed"""
+    from detzero_b200.det.dataset import synth_waymo_cloud
+    model = _model(world, 'tf32', cuda, 'ds')
+    full = world['batches'][0]
+    sparse_pts = full['points'].copy()
+    sparse_pts[60000:, 1:4] = 1.0e4                       # two thirds of the points leave the range: far fewer voxels
+    sparse = dict(full, points=sparse_pts)
+    for _ in range(3):
+        _settle(model, lambda: _bd(sparse, cuda))
+    static = _bd(sparse, cuda)
+    g, out = model.capture_graph(static, warmup=1)
+    g.replay()
+    model.post_processing(out)                            # the sparse frame fits
+    static['points'].copy_(torch.from_numpy(full['points']))
+    g.replay()
+    with pytest.raises(RuntimeError, match='overflow'):
+        model.post_processing(out)
+    _settle(model, lambda: _bd(full, cuda))               # hints were raised: the eager re-run settles and succeeds
+    with torch.no_grad():
+        pred, _ = model(_bd(full, cuda))
+    assert pred[0]['pred_boxes'].shape[0] > 0

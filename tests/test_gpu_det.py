@@ -424,9 +424,6 @@ def _assert_same_detections(got, want):
     assert nearest[0].max().item() < 1e-3
 
 
-@pytest.mark.xfail(strict=False, reason='KNOWN ISSUE (round 1): fails in ~1 of 6 full-suite runs, box-dependent and then persistent within the '
-                                       'process (suspected read of never-written memory behind the large dynamic-VFE capacities); '
-                                       'DESIGN.md section 7')
 def test_dynamic_vfe_into_backbone(cuda):
     """BASELINE configs[2] path (multi-sweep): DynamicMeanVFE (key order b,x,y,z) -> VoxelResBackBone8x; the backbone builds
     its grid index from the arbitrary-order coordinate list"""
@@ -454,16 +451,9 @@ def test_dynamic_vfe_into_backbone(cuda):
         checks['output features'] = checks['output sites'] and util.rel_err(got.features.cpu(), want['out'].f) < 1e-4
         return [k for k, ok in checks.items() if not ok]
 
-    # KNOWN ISSUE (round 1): this chain failed in 3 of ~18 full-suite runs, each time on a freshly started box, and then on the
-    # retry inside the same process as well, while 4 x 46 tests ran green back to back on another box: box-dependent and
-    # persistent within a process, i.e. most likely a read of memory that is never written and usually happens to be zero
-    # (this test has by far the largest capacities of the suite: cap = number of points).  Marked xfail(strict=False) so the
-    # suite keeps running; the failing checks are printed.
+    # round 1 saw an intermittent failure here: id()-keyed global caches of folded BN / packed weights handed a freed model's
+    # tensors to the next model; the caches now live on the modules.  No retry, no xfail.
     failed = attempt()
-    if failed:
-        print('test_dynamic_vfe_into_backbone: FIRST ATTEMPT FAILED checks %s -- retrying once' % failed)
-        torch.cuda.synchronize()
-        failed = attempt()
     assert not failed, failed
 
 

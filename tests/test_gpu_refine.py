@@ -84,21 +84,28 @@ def test_prm_vs_reference_golden(cuda, mode, tol):
     assert (got[valid][:, :6] - want[valid][:, :6]).abs().max().item() < tol     # refined boxes <= 1e-3 in fp32
 
 
-def test_grm_vs_reference_golden(cuda):
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-3), ('tf32', 3e-2)])
+def test_grm_vs_reference_golden(cuda, mode, tol):
+    """fp32: the exact-FMA kernels; tf32: the tcgen05 linears + attention the production configuration runs"""
     from detzero_b200.refine import GeometryTransformer
-    m = GeometryTransformer(ri.grm_cfg(), 11, 4).eval()
+    cfg = ri.grm_cfg()
+    cfg.COMPUTE_MODE = mode
+    m = GeometryTransformer(cfg, 11, 4).eval()
     weights.load_seeded(m, SEED + 1)
     m = m.to(cuda)
     d = m(_to(ri.grm_inputs(SEED + 1), cuda))
-    assert util.rel_err(m.preds_dict['geometry_cls'].cpu(), GOLD['grm.geometry_cls']) < 1e-3
-    assert util.rel_err(m.preds_dict['geometry_reg'].cpu(), GOLD['grm.geometry_reg']) < 1e-3
-    assert (d['batch_box_preds'].cpu() - torch.from_numpy(GOLD['grm.batch_box_preds'])).abs().max().item() < 1e-3
+    assert util.rel_err(m.preds_dict['geometry_cls'].cpu(), GOLD['grm.geometry_cls']) < tol
+    assert util.rel_err(m.preds_dict['geometry_reg'].cpu(), GOLD['grm.geometry_reg']) < tol
+    assert (d['batch_box_preds'].cpu() - torch.from_numpy(GOLD['grm.batch_box_preds'])).abs().max().item() < (1e-3 if mode == 'fp32' else 0.1)    # reg * anchor (<= 10 m)
 
 
-def test_crm_vs_reference_golden(cuda):
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('tf32', 5e-3)])
+def test_crm_vs_reference_golden(cuda, mode, tol):
     from detzero_b200.refine import ConfidencePointnet
-    m = ConfidencePointnet(ri.crm_cfg(), 32, 32).eval()
+    cfg = ri.crm_cfg()
+    cfg.COMPUTE_MODE = mode
+    m = ConfidencePointnet(cfg, 32, 32).eval()
     weights.load_seeded(m, SEED + 2)
     m = m.to(cuda)
     d = m(_to(ri.crm_inputs(SEED + 2), cuda))
-    assert (d['pred_score'].cpu() - torch.from_numpy(GOLD['crm.pred_score'])).abs().max().item() < 1e-4
+    assert (d['pred_score'].cpu() - torch.from_numpy(GOLD['crm.pred_score'])).abs().max().item() < tol

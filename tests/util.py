@@ -40,38 +40,7 @@ def clustered_cloud(n, seed, pc_range=SMALL_RANGE, c=5):
     return np.concatenate([p, f], axis=1).astype(np.float32)
 
 
-def model_cfg(backbone='VoxelResBackBone8x', mode='fp32', channels=None):
-    cfg = AttrDict({
-        'NAME': 'CenterPoint', 'SECOND_STAGE': False,
-        'VFE': {'NAME': 'MeanVFE'},
-        'BACKBONE_3D': {'NAME': backbone, 'COMPUTE_MODE': mode},
-        'MAP_TO_BEV': {'NAME': 'HeightCompression', 'NUM_BEV_FEATURES': 256},
-        'BACKBONE_2D': {'NAME': 'BaseBEVBackbone', 'LAYER_NUMS': [5, 5], 'LAYER_STRIDES': [1, 2],
-                        'NUM_FILTERS': [128, 256], 'UPSAMPLE_STRIDES': [1, 2], 'NUM_UPSAMPLE_FILTERS': [256, 256],
-                        'COMPUTE_MODE': mode},
-        'DENSE_HEAD': {
-            'NAME': 'CenterHead', 'CLASS_AGNOSTIC': False, 'COMPUTE_MODE': mode,
-            'CLASS_NAMES_EACH_HEAD': [['Vehicle', 'Pedestrian', 'Cyclist']],
-            'SHARED_CONV_CHANNEL': 64, 'USE_BIAS_BEFORE_NORM': True, 'NUM_HM_CONV': 2, 'IOU_WEIGHT': 1,
-            'SEPARATE_HEAD_CFG': {
-                'HEAD_ORDER': ['center', 'center_z', 'dim', 'rot', 'iou'],
-                'HEAD_DICT': {'center': {'out_channels': 2, 'num_conv': 2}, 'center_z': {'out_channels': 1, 'num_conv': 2},
-                              'dim': {'out_channels': 3, 'num_conv': 2}, 'rot': {'out_channels': 2, 'num_conv': 2},
-                              'iou': {'out_channels': 1, 'num_conv': 2}}},
-            'TARGET_ASSIGNER_CONFIG': {'FEATURE_MAP_STRIDE': 8, 'NUM_MAX_OBJS': 500, 'GAUSSIAN_OVERLAP': 0.1, 'MIN_RADIUS': 2},
-            'POST_PROCESSING': {'SCORE_THRESH': 0.03, 'POST_CENTER_LIMIT_RANGE': [-80, -80, -10.0, 80, 80, 10.0],
-                                'MAX_OBJ_PER_SAMPLE': 500,
-                                'NMS_CONFIG': {'NMS_TYPE': 'nms_gpu', 'NMS_THRESH': 0.7, 'NMS_PRE_MAXSIZE': 4096,
-                                               'NMS_POST_MAXSIZE': 500}}},
-        'POST_PROCESSING': {'RECALL_THRESH_LIST': [0.3, 0.5, 0.7], 'SCORE_THRESH': 0.03, 'OUTPUT_RAW_SCORE': False,
-                            'EVAL_METRIC': 'waymo'},
-    })
-    if channels is not None:
-        cfg.BACKBONE_3D.CHANNELS = channels
-    return cfg
-
-
-CLASS_NAMES = ['Vehicle', 'Pedestrian', 'Cyclist']
+from detzero_b200.synthetic import model_cfg, CLASS_NAMES    # noqa: E402,F401  (one definition, shared with bench.py)
 
 
 def rel_err(a, b):
