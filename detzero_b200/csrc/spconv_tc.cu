@@ -245,8 +245,8 @@ k_spconv_tf32(const __grid_constant__ CUtensorMap tmW, const float* __restrict__
     if (warp == Cfg::PRODUCERS) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-static long long* g_dbgbuf = nullptr;
-static bool g_trace_on = false;
+long long* g_dbgbuf = nullptr;          // shared with spconv_bf16.cu (clock traces, tools/trace_*.py)
+bool g_trace_on = false;
 extern "C" int dz_debug_trace(long long* host, int n) {      // clock-trace helper for tools/trace_spconv.py (not part of the public header)
     if (!g_dbgbuf) { if (cudaMalloc(&g_dbgbuf, 4096 * 8) != cudaSuccess) return -1; cudaMemset(g_dbgbuf, 0, 4096 * 8); g_trace_on = true; return 1; }
     cudaDeviceSynchronize();

@@ -95,7 +95,7 @@ class HeightCompression(nn.Module):
     def forward(self, batch_dict):
         t = batch_dict['encoded_spconv_tensor']
         D, H, W = t.spatial_shape
-        nhwc = ops.sparse_to_bev(t._feat, t._idx, t._count, t._cap, t.batch_size, D, H, W)   # channel = c*D + z
+        nhwc = ops.sparse_to_bev(t._feat, t._idx, t._count, t._cap, t.batch_size, D, H, W, planes=t._planes)   # channel = c*D + z
         batch_dict['spatial_features'] = _nchw_view(nhwc)          # (N, C*D, H, W), channels_last memory
         batch_dict['spatial_features_stride'] = batch_dict['encoded_spconv_tensor_stride']
         return batch_dict

@@ -164,27 +164,39 @@ def new_sched_ws(cap, device):
     return torch.empty(int(lib().dz_rulebook_schedule_ws_bytes(cap)), dtype=torch.uint8, device=device)
 
 
-def rulebook_subm(coords, d_n, cap, index, ksize, layout='k', sched_ws=None):
+def rulebook_subm(coords, d_n, cap, index, ksize, layout='k', sched_ws=None, frame_major=False):
     """layout 'k': k-major (K, cap) table (exact-fp32 kernel, parity tests); 'row': row-major (cap, 32) table for the
     tensor-core kernels; 'both': (nbr, tab).  sched_ws (row/both only): also leave the tile-schedule digests there."""
     K = ksize[0] * ksize[1] * ksize[2]
     nbr = torch.empty((K, cap), dtype=torch.int32, device=coords.device) if layout in ('k', 'both') else None
     tab = torch.empty((cap, 32), dtype=torch.int32, device=coords.device) if layout in ('row', 'both') else None
     check(lib().dz_rulebook_subm(_p(coords), _p(d_n), cap, index.B, *index.dhw, iarr(ksize), _p(index.bitmap),
-                                 _p(index.prefix), _p(index.perm), _p(nbr), _p(tab), _p(sched_ws), _stream()), 'rulebook_subm')
+                                 _p(index.prefix), _p(index.perm), _p(nbr), _p(tab), _p(sched_ws), int(bool(frame_major)), _stream()),
+          'rulebook_subm')
     _count(1 if sched_ws is None else 2)
     return nbr if layout == 'k' else tab if layout == 'row' else (nbr, tab)
 
 
-def rulebook_schedule(tab, d_n, sched_ws):
+def rulebook_schedule(tab, d_n, sched_ws, B=1, frame_major=False, K=None):
     """tile schedule for the tensor-core conv from the scratch the rulebook call filled: returns `order`
-    (cap + ceil(cap/128),) = row order | tile launch order; see dz_rulebook_schedule"""
+    (cap + ceil(cap/128),) = row order | tile launch order; see dz_rulebook_schedule.  frame_major (same value as in the
+    rulebook call): rows sorted by (frame, mask), tiles ordered frame by frame"""
     _need_cuda(tab)
     cap = tab.shape[0]
-    order = torch.empty(cap + (cap + 127) // 128, dtype=torch.int32, device=tab.device)
-    check(lib().dz_rulebook_schedule(_p(tab), cap, _p(d_n), _p(order), _p(sched_ws), sched_ws.numel(), _stream()), 'rulebook_schedule')
-    _count(1)
-    return order
+    tiles = (cap + 127) // 128
+    if K is None:                                       # row order | tile order
+        order = torch.empty(cap + tiles, dtype=torch.int32, device=tab.device)
+        check(lib().dz_rulebook_schedule(_p(tab), cap, _p(d_n), _p(order), _p(sched_ws), sched_ws.numel(), int(B), int(bool(frame_major)),
+                                         0, None, _stream()), 'rulebook_schedule')
+        _count(1)
+        return order
+    # K given: also the TILE-major table (tiles, K+1, 128) for the persistent bf16-plane conv; order gets the tile masks appended
+    order = torch.empty(cap + 2 * tiles, dtype=torch.int32, device=tab.device)
+    tab_tiles = torch.empty((tiles, int(K) + 1, 128), dtype=torch.int32, device=tab.device)
+    check(lib().dz_rulebook_schedule(_p(tab), cap, _p(d_n), _p(order), _p(sched_ws), sched_ws.numel(), int(B), int(bool(frame_major)),
+                                     int(K), _p(tab_tiles), _stream()), 'rulebook_schedule')
+    _count(2)
+    return order, tab_tiles
 
 
 def table_to_rows(nbr):
@@ -202,7 +214,7 @@ def conv_out_dhw(in_dhw, ksize, stride, pad):
     return [(in_dhw[d] + 2 * pad[d] - (ksize[d] - 1) - 1) // stride[d] + 1 for d in range(3)]
 
 
-def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap, layout='k', sched_ws=None):
+def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap, layout='k', sched_ws=None, frame_major=False):
     dev = coords.device
     out_dhw = conv_out_dhw(in_index.dhw, ksize, stride, pad)
     out_index = GridIndex(in_index.B, out_dhw, dev)
@@ -215,7 +227,7 @@ def rulebook_conv(coords, d_n, in_cap, in_index, ksize, stride, pad, out_cap, la
     check(lib().dz_rulebook_conv(_p(coords), _p(d_n), in_cap, in_index.B, iarr(in_index.dhw), iarr(ksize), iarr(stride),
                                  iarr(pad), _p(in_index.bitmap), _p(in_index.prefix), _p(in_index.perm), _p(out_coords),
                                  _p(d_n_out), out_cap, _p(out_index.bitmap), _p(out_index.prefix), _p(nbr), _p(tab), _p(ws),
-                                 ws.numel(), _p(sched_ws), _stream()), 'rulebook_conv')
+                                 ws.numel(), _p(sched_ws), int(bool(frame_major)), _stream()), 'rulebook_conv')
     _count(6 if sched_ws is None else 7)
     return out_coords, d_n_out, out_index, (nbr if layout == 'k' else tab if layout == 'row' else (nbr, tab)), out_dhw
 
@@ -231,6 +243,11 @@ def pack_spconv_weight(w, mode):
     if cin_pad != cin:
         w = torch.nn.functional.pad(w, (0, cin_pad - cin))
     w = w.reshape(cout, -1).contiguous()
+    if mode in _lib.PLANES:                           # bf16 planes: rows [w0 ; w1], w0 = RN_bf16(W), w1 = RN_bf16(W - w0)
+        w0 = w.to(torch.bfloat16)
+        if _lib.PLANES[mode] == 1:
+            return w0.contiguous()
+        return torch.cat([w0, (w - w0.float()).to(torch.bfloat16)], dim=0).contiguous()
     if mode == _lib.DZ_TF32X3:                        # (2, Cout, K*cin_pad): hi = RN_tf32(W), lo = RN_tf32(W - hi)
         hi = round_tf32(w)
         return torch.stack([hi, round_tf32(w - hi)]).contiguous()
@@ -246,7 +263,7 @@ def round_tf32(t):
 
 
 def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residual, relu, mode=_lib.DZ_F32, out=None,
-               d_n_in=None, kshape=None, row_order=None, layout=None):
+               d_n_in=None, kshape=None, row_order=None, layout=None, tab_tiles=None):
     """feats (in_cap, cin); weight_packed per pack_spconv_weight; kshape = (K, cin, cout).
     nbr: k-major (K, cap) table for DZ_F32; row-major (cap, 32) table for the tensor-core modes (a k-major table is
     converted on the fly); layout: 'k' | 'row' says which one `nbr` is (None: inferred from the shape, ambiguous only for
@@ -260,16 +277,31 @@ def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residu
         nbr = table_to_rows(nbr)
     elif mode == _lib.DZ_F32 and layout == 'row':
         raise RuntimeError('the exact-fp32 kernel needs the k-major (K, cap) table')
-    assert feats.shape[1] == cin and (nbr.shape[0] == K if mode == _lib.DZ_F32 else nbr.shape[1] == 32)
+    assert nbr.shape[0] == K if mode == _lib.DZ_F32 else nbr.shape[1] == 32
+    planes = _lib.PLANES.get(mode, 0)
+    if planes:
+        cin_pad = 8 if cin <= 8 else cin
+        assert feats.dtype == torch.bfloat16 and feats.is_contiguous() and feats.shape[1] == planes * cin_pad, (feats.dtype, feats.shape)
+        assert weight_packed.dtype == torch.bfloat16 and tuple(weight_packed.shape) == (planes * cout, K * cin_pad)
+        assert residual is None or (residual.dtype == torch.bfloat16 and residual.shape[1] == planes * cout)
+        if out is None:
+            out = torch.empty((out_cap, planes * cout), dtype=torch.bfloat16, device=feats.device)
+    else:
+        assert feats.shape[1] == cin
     if out is None:
         out = torch.empty((out_cap, cout), dtype=torch.float32, device=feats.device)
     if _trace is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, feats.shape[0], _p(nbr), K, nbr.shape[1] if mode == _lib.DZ_F32 else nbr.shape[0],
-                              _p(row_order), _p(d_n_out), out_cap,
-                              _p(_f32c(weight_packed)), _p(scale), _p(shift), _p(residual), int(relu), _p(out), cout,
-                              mode, _stream()), 'spconv_fwd')
+    if planes:
+        check(lib().dz_spconv_fwd_planes(_p(feats), cin, feats.shape[0], _p(nbr), K, nbr.shape[0], _p(row_order), _p(d_n_out), out_cap,
+                                         _p(weight_packed), _p(scale), _p(shift), _p(residual), int(relu), _p(out), cout, planes,
+                                         _p(tab_tiles if row_order is not None else None), _stream()), 'spconv_fwd_planes')
+    else:
+        check(lib().dz_spconv_fwd(_p(_f32c(feats)), cin, feats.shape[0], _p(nbr), K, nbr.shape[1] if mode == _lib.DZ_F32 else nbr.shape[0],
+                                  _p(row_order), _p(d_n_out), out_cap,
+                                  _p(_f32c(weight_packed)), _p(scale), _p(shift), _p(residual), int(relu), _p(out), cout,
+                                  mode, _stream()), 'spconv_fwd')
     _count(1)
     if _trace is not None:
         ev1.record()
@@ -281,14 +313,45 @@ def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residu
     return out
 
 
-def sparse_to_bev(feats, coords, d_n, cap, B, D, H, W, out=None):
-    c = feats.shape[1]
+def to_planes(x, d_n, planes, c_pad=None):
+    """fp32 (rows, c) -> bf16 operand planes (rows, planes * c_pad): row = [p0 | p1], p0 = RN_bf16(x), p1 = RN_bf16(x - p0)
+    (channels zero-padded to c_pad); rows >= *d_n are left untouched"""
+    _need_cuda(x)
+    rows, c = x.shape
+    c_pad = c if c_pad is None else int(c_pad)
+    out = torch.empty((rows, planes * c_pad), dtype=torch.bfloat16, device=x.device)
+    if rows:
+        check(lib().dz_to_planes(_p(_f32c(x)), _p(d_n), rows, c, c_pad, planes, _p(out), _stream()), 'to_planes')
+        _count(1)
+    return out
+
+
+def from_planes(x, d_n, planes):
+    """bf16 operand planes (rows, planes * c) -> fp32 (rows, c) = p0 (+ p1)"""
+    _need_cuda(x)
+    rows, c = x.shape[0], x.shape[1] // planes
+    out = torch.empty((rows, c), dtype=torch.float32, device=x.device)
+    if rows:
+        assert x.dtype == torch.bfloat16 and x.is_contiguous()
+        check(lib().dz_from_planes(_p(x), _p(d_n), rows, c, planes, _p(out), _stream()), 'from_planes')
+        _count(1)
+    return out
+
+
+def sparse_to_bev(feats, coords, d_n, cap, B, D, H, W, out=None, planes=0):
+    """planes = 0: fp32 (rows, c) features; 1 / 2: bf16 operand planes (rows, planes * c) -- always an fp32 NHWC map"""
+    c = feats.shape[1] // max(planes, 1)
     if out is None:
         out = torch.zeros((B, H, W, c * D), dtype=torch.float32, device=feats.device)
     else:
         out.zero_()
-    check(lib().dz_sparse_to_bev(_p(_f32c(feats)), _p(coords), _p(d_n), cap, c, B, D, H, W, _p(out), _stream()),
-          'sparse_to_bev')
+    if planes:
+        assert feats.dtype == torch.bfloat16 and feats.is_contiguous()
+        check(lib().dz_sparse_to_bev_planes(_p(feats), _p(coords), _p(d_n), cap, c, planes, B, D, H, W, _p(out), _stream()),
+              'sparse_to_bev_planes')
+    else:
+        check(lib().dz_sparse_to_bev(_p(_f32c(feats)), _p(coords), _p(d_n), cap, c, B, D, H, W, _p(out), _stream()),
+              'sparse_to_bev')
     _count(1)
     return out
 

@@ -14,6 +14,8 @@ B200-native differences (behaviour-preserving):
     strided-conv output sites are emitted sorted by (b,z,y,x) (spconv's order is implementation-defined)
   * in eval mode ``SparseSequential`` fuses conv + BatchNorm1d + ReLU (+ residual) into one launch.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -46,6 +48,7 @@ class SparseConvTensor:
         self._count = count
         self._n = n_host
         self._index = index
+        self._planes = 0            # 0: fp32 (rows, C) features; 1 / 2: bf16 operand planes (rows, planes*C), csrc/spconv_bf16.cu
 
     # ---- spconv-visible surface ---------------------------------------------------------------------------
     def num(self):
@@ -65,6 +68,9 @@ class SparseConvTensor:
 
     @property
     def features(self):
+        """(N, C) float32 features (spconv contract).  A tensor produced by a bf16-plane layer is converted on demand."""
+        if self._planes:
+            return ops.from_planes(self._feat, self._count, self._planes)[:self.num()]
         return self._feat[:self.num()]
 
     @features.setter
@@ -84,13 +90,14 @@ class SparseConvTensor:
             t._n = t._cap
             t._count = torch.full((1,), t._cap, dtype=torch.int32, device=new_features.device)
         t._feat = new_features
+        t._planes = 0
         return t
 
     def dense(self, channels_first=True):
         """(B, C, D, H, W) like spconv's .dense() (height_compression.py:21)"""
         D, H, W = self.spatial_shape
-        c = self._feat.shape[1]
-        nhwc = ops.sparse_to_bev(self._feat, self._idx, self._count, self._cap, self.batch_size, D, H, W)  # (B,H,W,c*D)
+        c = self._feat.shape[1] // max(self._planes, 1)
+        nhwc = ops.sparse_to_bev(self._feat, self._idx, self._count, self._cap, self.batch_size, D, H, W, planes=self._planes)  # (B,H,W,c*D)
         x = nhwc.view(self.batch_size, H, W, c, D)
         return x.permute(0, 3, 4, 1, 2).contiguous() if channels_first else x
 
@@ -101,11 +108,23 @@ class SparseConvTensor:
                                                      self.spatial_shape, with_perm=True)
         return self._index
 
-    def _like(self, feat):
+    def _like(self, feat, planes=0):
         t = SparseConvTensor.__new__(SparseConvTensor)
         t.__dict__.update(self.__dict__)
         t._feat = feat
+        t._planes = planes
         return t
+
+    def _as_planes(self, planes, c_pad):
+        """this tensor's features as bf16 operand planes (converted once per tensor if they are fp32)"""
+        if self._planes == planes:
+            return self._feat
+        if self._planes:
+            raise RuntimeError('a %d-plane tensor cannot feed a %d-plane layer: use one COMPUTE_MODE per backbone' % (self._planes, planes))
+        key = ('_as_planes', planes, c_pad)
+        if self.__dict__.get('_planes_cache', (None,))[0] != key:
+            self._planes_cache = (key, ops.to_planes(self._feat, self._count, planes, c_pad))
+        return self._planes_cache[1]
 
 
 class SparseModule(nn.Module):
@@ -144,6 +163,7 @@ class _RuleSubm:
         self.nbr = nbr             # k-major table (exact-fp32 kernel) or None
         self.tab = tab             # row-major table (tensor-core kernels) or None
         self.order = None          # tile schedule (tensor-core kernels)
+        self.tab_tiles = None      # tile-major scheduled table (persistent bf16-plane kernel)
         self.sched_ws = None       # mask digests + histogram left by the rulebook kernel
 
 
@@ -152,6 +172,7 @@ class _RuleConv:
         self.out_idx, self.d_n_out, self.out_index, self.out_dhw, self.out_cap = out_idx, d_n_out, out_index, out_dhw, out_cap
         self.nbr, self.tab = tables
         self.order = None
+        self.tab_tiles = None
         self.sched_ws = None
 
 
@@ -164,6 +185,8 @@ class _SparseConv(SparseModule):
     CAP_HEADROOM = 1.3
     #: build a tile schedule (rows grouped by neighbour mask) with every rulebook used by a tensor-core layer
     SCHEDULE_TILES = True
+    #: batches: sort the schedule by (frame, mask) so that the tiles in flight gather from ONE frame's (L2-resident) feature map
+    FRAME_MAJOR = bool(os.environ.get('DZ_FRAME_MAJOR'))      # measured (profiles/r02_spconv_notes.md): the 3 digest bits it costs outweigh the L2 gain
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
                  indice_key=None, subm=False, algo=None, mode='fp32'):
@@ -199,9 +222,11 @@ class _SparseConv(SparseModule):
             tc = _lib.MODES[self.mode] != _lib.DZ_F32
             layout = 'row' if tc else 'k'
             want = self._wants_schedule()
+            fm = self.FRAME_MAJOR and x.batch_size > 1
             if self.subm:
                 sws = ops.new_sched_ws(x._cap, x._idx.device) if want else None
-                t = ops.rulebook_subm(x._idx, x._count, x._cap, x.grid_index(), self.kernel_size, layout=layout, sched_ws=sws)
+                t = ops.rulebook_subm(x._idx, x._count, x._cap, x.grid_index(), self.kernel_size, layout=layout, sched_ws=sws,
+                                      frame_major=fm)
                 rule = _RuleSubm(None if tc else t, t if tc else None)
             else:
                 in_index = x.grid_index()
@@ -219,9 +244,10 @@ class _SparseConv(SparseModule):
                     out_cap = int(min(cells, max(128, (int(hint * self.CAP_HEADROOM) + 127) // 128 * 128)))
                 sws = ops.new_sched_ws(out_cap, x._idx.device) if want else None
                 oc, d_n_out, out_index, t, odhw = ops.rulebook_conv(x._idx, x._count, x._cap, in_index, self.kernel_size, self.stride,
-                                                                    self.padding, out_cap, layout=layout, sched_ws=sws)
+                                                                    self.padding, out_cap, layout=layout, sched_ws=sws, frame_major=fm)
                 rule = _RuleConv(oc, d_n_out, out_index, (None, t) if tc else (t, None), odhw, out_cap)
             rule.sched_ws = sws
+            rule.frame_major = fm
             if key is not None:
                 x.indice_dict[key] = rule
         if schedule:
@@ -235,7 +261,12 @@ class _SparseConv(SparseModule):
     def _schedule(self, rule, x):
         """tile schedule of a rulebook (once per rulebook; only the tensor-core kernels use it)"""
         if rule.order is None and rule.sched_ws is not None:
-            rule.order = ops.rulebook_schedule(rule.tab, x._count if self.subm else rule.d_n_out, rule.sched_ws)
+            d_n = x._count if self.subm else rule.d_n_out
+            fm = getattr(rule, 'frame_major', False)
+            if _lib.MODES[self.mode] in _lib.PLANES:        # persistent kernel: also the tile-major table (one bulk copy per tile)
+                rule.order, rule.tab_tiles = ops.rulebook_schedule(rule.tab, d_n, rule.sched_ws, x.batch_size, fm, K=self.kshape[0])
+            else:
+                rule.order = ops.rulebook_schedule(rule.tab, d_n, rule.sched_ws, x.batch_size, fm)
 
     def _table(self, rule):
         """(table, row_order) for this layer's kernel"""
@@ -255,14 +286,23 @@ class _SparseConv(SparseModule):
         mode = _lib.MODES[self.mode]
         nbr, order = self._table(rule)
         lay = 'k' if mode == _lib.DZ_F32 else 'row'
+        planes = _lib.PLANES.get(mode, 0)
+        if planes:                                       # bf16 operand planes: inputs converted once, outputs stay in planes
+            feat = x._as_planes(planes, 8 if self.in_channels <= 8 else self.in_channels)
+            res = None if residual is None else residual._as_planes(planes, self.out_channels)
+        else:
+            if x._planes or (residual is not None and residual._planes):
+                raise RuntimeError('a bf16-plane tensor cannot feed a %s layer: use one COMPUTE_MODE per backbone' % self.mode)
+            feat, res = x._feat, (None if residual is None else residual._feat)
         if self.subm:
-            out = ops.spconv_fwd(x._feat, nbr, x._count, x._cap, self.packed_weight(mode), scale, shift,
-                                 None if residual is None else residual._feat, relu, mode, kshape=self.kshape, row_order=order, layout=lay)
-            return x._like(out)
-        out = ops.spconv_fwd(x._feat, nbr, rule.d_n_out, rule.out_cap, self.packed_weight(mode), scale, shift, None,
-                             relu, mode, d_n_in=x._count, kshape=self.kshape, row_order=order, layout=lay)
+            out = ops.spconv_fwd(feat, nbr, x._count, x._cap, self.packed_weight(mode), scale, shift, res, relu, mode,
+                                 kshape=self.kshape, row_order=order, layout=lay, tab_tiles=rule.tab_tiles)
+            return x._like(out, planes)
+        out = ops.spconv_fwd(feat, nbr, rule.d_n_out, rule.out_cap, self.packed_weight(mode), scale, shift, None,
+                             relu, mode, d_n_in=x._count, kshape=self.kshape, row_order=order, layout=lay, tab_tiles=rule.tab_tiles)
         t = SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict,
                              count=rule.d_n_out, n_host=None, index=rule.out_index)
+        t._planes = planes
         t._producer = self
         return t
 
@@ -317,6 +357,8 @@ class SparseSequential(SparseModule):
                 x = m(x)
                 i += 1
             else:
+                if x._planes:
+                    raise RuntimeError('plain nn.Modules cannot act on a bf16-plane tensor (only the fused eval path supports the bf16 modes)')
                 x = x._like(m(x._feat))        # acts on all capacity rows; rows beyond the count are never read
                 i += 1
         return x

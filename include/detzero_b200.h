@@ -28,8 +28,10 @@ extern "C" {
 typedef void* dz_stream_t;           /* cudaStream_t */
 
 enum { DZ_OK = 0, DZ_ERR_ARG = -1, DZ_ERR_CUDA = -2, DZ_ERR_WORKSPACE = -3, DZ_ERR_UNSUPPORTED = -4 };
-enum { DZ_F32 = 0, DZ_TF32 = 1, DZ_BF16 = 2, DZ_TF32X3 = 3 };   /* arithmetic mode of GEMM-shaped kernels:
-   F32 = fp32 FMA; TF32 = one tcgen05 TF32 pass; TF32X3 = hi/lo split, 3 TF32 passes, fp32-level accuracy (sparse conv) */
+enum { DZ_F32 = 0, DZ_TF32 = 1, DZ_BF16 = 2, DZ_TF32X3 = 3, DZ_BF16X2 = 4 };   /* arithmetic mode of GEMM-shaped kernels:
+   F32 = fp32 FMA; TF32 = one tcgen05 TF32 pass; TF32X3 = hi/lo split, 3 TF32 passes, fp32-level accuracy (sparse conv);
+   BF16 / BF16X2 = bf16 operand planes (1 plane: bf16 storage; 2 planes: x = p0 + p1, 16 significand bits in 4 bytes,
+   fp32-level accuracy at the cost of one TF32 pass), sparse conv only: dz_spconv_fwd_planes */
 
 int         dz_version(void);
 int         dz_sm_arch(void);                      /* 100 : built for sm_100a */
@@ -105,7 +107,8 @@ int dz_voxelize_dynamic_mean(const float* points, int n, int c, int B,
  * dz_rulebook_schedule needs (mask digests, scanned histogram) there. */
 int dz_rulebook_subm(const int32_t* coords, const int* d_n, int cap, int B, int D, int H, int W,
                      const int* ksize3_host, const uint32_t* bitmap, const uint32_t* prefix,
-                     const int32_t* perm, int32_t* nbr, int32_t* tab, void* sched_ws, dz_stream_t stream);
+                     const int32_t* perm, int32_t* nbr, int32_t* tab, void* sched_ws, int sched_frame_major,
+                     dz_stream_t stream);
 /* Strided conv: generates the output site set (sorted ascending (b,z,y,x)), its grid index and the table(s).
  * out_bitmap must be zero on entry. */
 int dz_rulebook_conv(const int32_t* in_coords, const int* d_n_in, int in_cap, int B,
@@ -113,15 +116,22 @@ int dz_rulebook_conv(const int32_t* in_coords, const int* d_n_in, int in_cap, in
                      const int* pad3_host, const uint32_t* in_bitmap, const uint32_t* in_prefix,
                      const int32_t* in_perm, int32_t* out_coords, int* d_n_out, int out_cap,
                      uint32_t* out_bitmap, uint32_t* out_prefix, int32_t* nbr, int32_t* tab,
-                     void* ws, size_t ws_bytes, void* sched_ws, dz_stream_t stream);
+                     void* ws, size_t ws_bytes, void* sched_ws, int sched_frame_major, dz_stream_t stream);
 /* Tile schedule for the tensor-core conv (no reference counterpart; spconv's implicit-GEMM "mask sort" plays the same
  * role).  order (cap + ceil(cap/128) ints): order[p] = output row at tile position p -- rows with alike neighbour
  * masks become adjacent, so a 128-row tile skips the kernel offsets none of its rows uses -- and order[cap + j] = the
  * tile the j-th CTA takes (most live offsets first).  Hand it to dz_spconv_fwd as row_order; results are bit-identical
- * to the unscheduled call.  sched_ws must be the one the rulebook call filled for this tab. */
+ * to the unscheduled call.  sched_ws must be the one the rulebook call filled for this tab.
+ * sched_frame_major (same value in the rulebook call and here; B = frames in the batch): sort by (frame, mask) and order the
+ * tiles frame by frame (heaviest first inside a frame), so that the rows the CTAs gather at any moment belong to ONE frame's
+ * feature map and stay L2-resident at batch sizes whose level no longer fits L2. */
 size_t dz_rulebook_schedule_ws_bytes(int cap);
 int dz_rulebook_schedule(const int32_t* tab, int cap, const int* d_n, int32_t* order, void* sched_ws,
-                         size_t ws_bytes, dz_stream_t stream);
+                         size_t ws_bytes, int B, int sched_frame_major, int K, int32_t* tab_tiles, dz_stream_t stream);
+/* tab_tiles (optional; ceil(cap/128) * (K+1) * 128 ints): the scheduled table again, TILE-major: tile j = (K+1) planes of 128
+ * ints, plane k < K = neighbour row of tile position p through offset k, plane K = the output row order[j*128+p] (-1 beyond the
+ * count).  With it `order` must have cap + 2*ceil(cap/128) ints: order[cap + tiles + j] = OR of tile j's row masks.  The
+ * persistent bf16-plane conv (dz_spconv_fwd_planes) fetches a tile's block with ONE bulk copy. */
 
 /* ---- sparse convolution -------------------------------------------------------------------------------- */
 /* out[o,:] = act( (sum_k in[nbr[k][o],:] @ W[k]) * scale + shift (+ residual[o,:]) )
@@ -136,11 +146,28 @@ int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_t* nbr, int
                   int out_cap, const float* weight, const float* scale, const float* shift,
                   const float* residual, int relu, float* out, int cout, int mode, dz_stream_t stream);
 
+/* The same layer on bf16 operand PLANES (modes DZ_BF16: planes = 1, DZ_BF16X2: planes = 2), csrc/spconv_bf16.cu: a persistent
+ * warp-specialised tcgen05 kernel.  Feature tensors `in`, `residual`, `out` are (rows, planes * C) bf16, a row = [p0 | p1] with
+ * x ~ p0 (+ p1), p0 = RN_bf16(x), p1 = RN_bf16(x - p0); cin <= 8 is stored padded to 8 channels per plane.  weight: (planes * cout,
+ * K * cin_pad) bf16, rows [w0 ; w1] split the same way.  tab = ROW-major table, row_order = NULL or the tile schedule,
+ * tab_tiles = NULL or the tile-major table dz_rulebook_schedule wrote next to row_order (fast path).
+ * No reference counterpart for the storage format (spconv keeps fp32 rows); dz_to_planes / dz_from_planes convert at the
+ * boundary: out[r, p, 0..c_pad) <- x[r, 0..c) (zero padded), x[r, c] <- p0 + p1. */
+int dz_spconv_fwd_planes(const void* in, int cin, int in_rows, const int32_t* tab, int K, int tab_rows,
+                         const int32_t* row_order, const int* d_n_out, int out_cap, const void* weight,
+                         const float* scale, const float* shift, const void* residual, int relu, void* out, int cout,
+                         int planes, const int32_t* tab_tiles, dz_stream_t stream);
+int dz_to_planes(const float* x, const int* d_n, int cap, int c, int c_pad, int planes, void* out, dz_stream_t stream);
+int dz_from_planes(const void* x, const int* d_n, int cap, int c, int planes, float* out, dz_stream_t stream);
+
 /* ---- BEV ------------------------------------------------------------------------------------------------ */
 /* SparseConvTensor.dense() + reshape(N, C*D, H, W) (height_compression.py:20-25) into NHWC:
  * out[b,y,x,c*D+z] = feats[i,c].  out must be zero on entry. */
 int dz_sparse_to_bev(const float* feats, const int32_t* coords, const int* d_n, int cap, int c,
                      int B, int D, int H, int W, float* out, dz_stream_t stream);
+/* the same from a bf16 planes tensor (rows, planes * c) */
+int dz_sparse_to_bev_planes(const void* feats, const int32_t* coords, const int* d_n, int cap, int c, int planes,
+                            int B, int D, int H, int W, float* out, dz_stream_t stream);
 /* NHWC conv2d (cross-correlation) with fused per-channel affine (folded BatchNorm2d / bias) and ReLU; output
  * written at channel offset into a tensor with out_cstride channels (fused torch.cat, backbone2d.py:107-108).
  * weight packed (KH, KW, cin, cout).  Replaces nn.Conv2d(+ZeroPad2d)+BatchNorm2d+ReLU stacks at

@@ -18,8 +18,12 @@ POST = dict(MAX_OBJ_PER_SAMPLE=500, SCORE_THRESH=0.03, POST_CENTER_LIMIT_RANGE=[
             NMS_THRESH=0.7, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=500)
 #: per-level feature bound vs the fp32 oracle, per sparse-conv mode (rel. to the level's max |feature|)
 LEVEL_TOL = {'fp32': 2e-5, 'tf32x3': 2e-4, 'bf16x2': 2e-4, 'tf32': 5e-3, 'bf16': 3e-2}
-#: modes whose detections must equal the oracle's (count, scores 1e-5, boxes 1e-3); the others: >= 90 % within 5 cm
+#: fp32-level sparse modes: with exact-fp32 dense convs the detections must equal the oracle's (count, scores, boxes within
+#: the stated bounds).  With the default TF32 dense convs (the reference's own cuDNN default) and for the
+#: reduced-precision sparse modes: >= 90 % of the oracle boxes within 5 cm / 0.05 rad / 0.02 score.
 EXACT_MODES = ('fp32', 'tf32x3', 'bf16x2')
+DET_TOL = {'fp32': dict(score_tol=1e-5, box_tol=1e-3, count_slack=0), 'tf32x3': dict(score_tol=1e-4, box_tol=2e-3, count_slack=2),
+           'bf16x2': dict(score_tol=1e-4, box_tol=2e-3, count_slack=2)}
 
 
 def _modes():
@@ -91,7 +95,7 @@ def _split_level(t, B):
     return [(idx[idx[:, 0] == b][:, 1:], f[torch.from_numpy(idx[:, 0] == b)]) for b in range(B)]
 
 
-def _check_against_oracle(world, mode, batch_dict, pred, frame_ids):
+def _check_against_oracle(world, mode, batch_dict, pred, frame_ids, dense_exact=False):
     B = len(frame_ids)
     for name in ('x_conv1', 'x_conv2', 'x_conv3', 'x_conv4', 'out'):
         t = batch_dict['encoded_spconv_tensor'] if name == 'out' else batch_dict['multi_scale_3d_features'][name]
@@ -101,8 +105,8 @@ def _check_against_oracle(world, mode, batch_dict, pred, frame_ids):
             assert util.rel_err(f, w.f) < LEVEL_TOL[mode], (mode, name, b, util.rel_err(f, w.f))
     for b in range(B):
         want = world['frames'][frame_ids[b]]['boxes']
-        if mode in EXACT_MODES:
-            _assert_same_detections(pred[b], want)
+        if mode in EXACT_MODES and dense_exact:
+            _assert_same_detections(pred[b], want, **DET_TOL[mode])
         else:
             ga, gb = pred[b], want
             assert abs(ga['pred_boxes'].shape[0] - gb['pred_boxes'].shape[0]) <= max(3, gb['pred_boxes'].shape[0] // 20)
@@ -117,12 +121,15 @@ def _check_against_oracle(world, mode, batch_dict, pred, frame_ids):
 def test_full_lattice_single_frame_vs_oracle(cuda, world, mode):
     if mode not in _modes():
         pytest.skip('mode %s not built' % mode)
-    model = _model(world, mode, cuda, 'ds')
-    pred, _ = _settle(model, lambda: _bd(world['batches'][0], cuda))
-    with torch.no_grad():
-        bd = model.forward_device(_bd(world['batches'][0], cuda))
-        pred, _ = model.post_processing(bd)
-    _check_against_oracle(world, mode, bd, pred, [0])
+    for dense_mode in (['fp32', 'tf32'] if mode in EXACT_MODES else ['tf32']):
+        if mode == 'fp32' and dense_mode == 'tf32':
+            continue
+        model = _model(world, mode, cuda, 'ds', dense_mode=dense_mode)
+        pred, _ = _settle(model, lambda: _bd(world['batches'][0], cuda))
+        with torch.no_grad():
+            bd = model.forward_device(_bd(world['batches'][0], cuda))
+            pred, _ = model.post_processing(bd)
+        _check_against_oracle(world, mode, bd, pred, [0], dense_exact=(dense_mode == 'fp32'))
 
 
 @pytest.mark.parametrize('mode', ['tf32x3', 'bf16x2', 'tf32', 'bf16'])

@@ -139,6 +139,36 @@ def test_spconv_fwd_fp32(cuda, cin, cout):
         out = ops.spconv_fwd(t._feat, nbr, t._count, n, wp, scale.to(cuda), shift.to(cuda), res.to(cuda), True, mode,
                              kshape=(27, cin, cout))
         assert util.rel_err(out.cpu(), ref) < tol, mode
+    # bf16 operand planes (persistent tcgen05 kernel): 2 planes = fp32-level, 1 plane = bf16 storage
+    tab = ops.table_to_rows(nbr)
+    cin_pad = 8 if cin <= 8 else cin
+    for mode, tol in ((_lib.DZ_BF16X2, 2e-5), (_lib.DZ_BF16, 1e-2)):
+        P = _lib.PLANES[mode]
+        wp = ops.pack_spconv_weight(w, mode).to(cuda)
+        fp = ops.to_planes(t._feat, t._count, P, cin_pad)
+        rp = ops.to_planes(res.to(cuda), t._count, P)
+        out = ops.spconv_fwd(fp, tab, t._count, n, wp, scale.to(cuda), shift.to(cuda), rp, True, mode, kshape=(27, cin, cout), layout='row')
+        assert out.dtype == torch.bfloat16 and out.shape == (n, P * cout)
+        assert util.rel_err(ops.from_planes(out, t._count, P).cpu(), ref) < tol, mode
+
+
+def test_planes_roundtrip(cuda):
+    """fp32 <-> bf16 operand planes: p0 = RN_bf16(x), p1 = RN_bf16(x - p0); 2 planes keep 16 significand bits, channels are
+    zero-padded, rows beyond the device count are left alone"""
+    from detzero_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(1000, 5, generator=g) * torch.logspace(-3, 3, 1000)[:, None]).to(cuda)
+    d_n = torch.tensor([900], dtype=torch.int32, device=cuda)
+    for P in (1, 2):
+        pl = ops.to_planes(x, d_n, P, 8)
+        assert pl.shape == (1000, P * 8)
+        p0 = pl[:900, :5].float()
+        assert torch.equal(p0, x[:900].to(torch.bfloat16).float())
+        assert torch.all(pl[:900, 5:8] == 0)
+        if P == 2:
+            assert torch.equal(pl[:900, 8:13].float(), (x[:900] - p0).to(torch.bfloat16).float())
+        back = ops.from_planes(pl, d_n, P)[:900, :5]
+        assert ((back - x[:900]).abs() <= x[:900].abs() * (2.0 ** -8 if P == 1 else 2.0 ** -16)).all()
 
 
 @pytest.mark.parametrize('subm,cin,cout', [(True, 16, 16), (True, 64, 64), (False, 32, 64)])
@@ -167,7 +197,7 @@ def test_tile_schedule_is_a_bit_exact_permutation(cuda, subm, cin, cout):
     bits = ((k_major >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
     assert np.array_equal(tab[:n, 27].cpu().numpy().astype(np.int64), bits)
     assert torch.equal(ops.table_to_rows(nbr)[:n], tab[:n])
-    order = ops.rulebook_schedule(tab, d_n, sws)
+    order, tab_tiles = ops.rulebook_schedule(tab, d_n, sws, K=27)
     o = order[:n].cpu().numpy()
     assert np.array_equal(np.sort(o), np.arange(n))
     tiles = (cap + 127) // 128
@@ -180,6 +210,15 @@ def test_tile_schedule_is_a_bit_exact_permutation(cuda, subm, cin, cout):
         return v.reshape(27, tiles, 128).any(2).sum(0)
     work = tile_work(k_major[:, o] >= 0)
     assert np.all(np.diff(work[to]) <= 0)
+    # tile-major copy of the scheduled table: tile j = 27 neighbour planes + the row plane; tile masks appended to `order`
+    tn = (n + 127) // 128
+    tt = tab_tiles[:tn].cpu().numpy()
+    rows_plane = np.full(tn * 128, -1, np.int64); rows_plane[:n] = o
+    assert np.array_equal(tt[:, 27, :].reshape(-1), rows_plane)
+    want_planes = np.full((27, tn * 128), -1, np.int64); want_planes[:, :n] = k_major[:, o]
+    assert np.array_equal(tt[:, :27, :].transpose(1, 0, 2).reshape(27, -1), want_planes)
+    tmask = order[cap + tiles:cap + 2 * tiles].cpu().numpy()[:tn]
+    assert np.array_equal(tmask, (((want_planes >= 0).reshape(27, tn, 128).any(2)).astype(np.int64) << np.arange(27)[:, None]).sum(0))
     assert work.sum() <= tile_work(k_major >= 0).sum()
     g = np.random.default_rng(9)
     w = torch.from_numpy(g.normal(0, 0.2, (cout, 3, 3, 3, cin)).astype(np.float32))
@@ -196,6 +235,17 @@ def test_tile_schedule_is_a_bit_exact_permutation(cuda, subm, cin, cout):
                            out=torch.full((out_cap, cout), -7.0, device=cuda))      # k-major table converted on the fly
         assert torch.equal(a, b) and torch.equal(a, c), mode
         assert torch.all(a[n:] == -7.0)
+    for mode in (_lib.DZ_BF16X2, _lib.DZ_BF16):           # persistent bf16-plane kernel: scheduled == unscheduled, bit for bit
+        P = _lib.PLANES[mode]
+        wp = ops.pack_spconv_weight(w, mode).to(cuda)
+        fp, rp = ops.to_planes(t._feat, t._count, P), ops.to_planes(res, d_n, P)
+        fill = lambda: torch.full((out_cap, P * cout), -7.0, device=cuda, dtype=torch.bfloat16)
+        a = ops.spconv_fwd(fp, tab, d_n, out_cap, wp, scale, shift, rp, True, mode, kshape=(27, cin, cout), out=fill(), layout='row')
+        b = ops.spconv_fwd(fp, tab, d_n, out_cap, wp, scale, shift, rp, True, mode, kshape=(27, cin, cout), out=fill(), row_order=order, layout='row')
+        c = ops.spconv_fwd(fp, tab, d_n, out_cap, wp, scale, shift, rp, True, mode, kshape=(27, cin, cout), out=fill(), row_order=order, layout='row',
+                           tab_tiles=tab_tiles)                              # fast path: one bulk copy per tile
+        assert torch.equal(a, b) and torch.equal(a, c), mode
+        assert torch.all(a[n:] == -7.0) and torch.all(c[n:] == -7.0)
     with pytest.raises(RuntimeError):         # the exact-fp32 kernel compacts per offset itself: a schedule is refused loudly
         ops.spconv_fwd(t._feat, nbr, d_n, out_cap, ops.pack_spconv_weight(w, _lib.DZ_F32).to(cuda), scale, shift, res, True,
                        _lib.DZ_F32, kshape=(27, cin, cout), row_order=order)
@@ -203,7 +253,9 @@ def test_tile_schedule_is_a_bit_exact_permutation(cuda, subm, cin, cout):
 
 @pytest.mark.parametrize('kind,mode,tol', [('VoxelBackBone8x', 'fp32', 2e-5), ('VoxelResBackBone8x', 'fp32', 2e-5),
                                            ('VoxelBackBone8x', 'tf32', 5e-3), ('VoxelResBackBone8x', 'tf32', 5e-3),
-                                           ('VoxelBackBone8x', 'tf32x3', 2e-4), ('VoxelResBackBone8x', 'tf32x3', 2e-4)])
+                                           ('VoxelBackBone8x', 'tf32x3', 2e-4), ('VoxelResBackBone8x', 'tf32x3', 2e-4),
+                                           ('VoxelBackBone8x', 'bf16x2', 2e-4), ('VoxelResBackBone8x', 'bf16x2', 2e-4),
+                                           ('VoxelBackBone8x', 'bf16', 3e-2), ('VoxelResBackBone8x', 'bf16', 3e-2)])
 def test_backbone3d_vs_oracle(cuda, kind, mode, tol):
     from detzero_b200.det import cp_modules
     cfg = util.model_cfg(kind).BACKBONE_3D
@@ -410,18 +462,26 @@ def test_centerpoint_end_to_end(cuda):
         _assert_same_detections(pred_dicts[b], want[b])
 
 
-def _assert_same_detections(got, want):
-    """same detections up to the order of (near-)tied scores: counts equal, sorted scores equal, every oracle box has a
-    product box within 1e-3 m / rad (+1e-4 relative: exp() of the size regressions)"""
-    assert got['pred_boxes'].shape[0] == want['pred_boxes'].shape[0]
+def _assert_same_detections(got, want, score_tol=1e-5, box_tol=1e-3, count_slack=0):
+    """same detections up to the order of (near-)tied scores: counts equal (up to `count_slack` boxes that sit on the score /
+    NMS thresholds in the reduced-precision modes), sorted scores equal, every oracle box has a product box within box_tol
+    m / rad (+1e-4 relative: exp() of the size regressions)"""
+    ng, nw = got['pred_boxes'].shape[0], want['pred_boxes'].shape[0]
+    assert abs(ng - nw) <= count_slack, (ng, nw)
     gs, ws = got['pred_scores'].cpu().sort(descending=True)[0], want['pred_scores'].sort(descending=True)[0]
-    assert (gs - ws).abs().max().item() < 1e-5
+    if count_slack == 0:
+        assert (gs - ws).abs().max().item() < score_tol
     # the label is part of the match: one BEV cell can fire for two classes with the very same box
-    gb = torch.cat([got['pred_boxes'].cpu().double(), got['pred_labels'].cpu().double()[:, None]], dim=1)
-    wb = torch.cat([want['pred_boxes'].double(), want['pred_labels'].double()[:, None]], dim=1)
-    diff = (gb[None, :, :] - wb[:, None, :]).abs() / (1.0 + 0.1 * wb[:, None, :].abs())
-    nearest = diff.max(dim=2)[0].min(dim=1)
-    assert nearest[0].max().item() < 1e-3
+    gb = torch.cat([got['pred_boxes'].cpu().double(), got['pred_scores'].cpu().double()[:, None] * (box_tol / score_tol),
+                    got['pred_labels'].cpu().double()[:, None]], dim=1)
+    wb = torch.cat([want['pred_boxes'].double(), want['pred_scores'].double()[:, None] * (box_tol / score_tol),
+                    want['pred_labels'].double()[:, None]], dim=1)
+    scale = 1.0 + 0.1 * wb[:, None, :].abs()
+    scale[..., 7] = 1.0                                     # the (rescaled) score is compared absolutely
+    diff = (gb[None, :, :] - wb[:, None, :]).abs() / scale
+    nearest = diff.max(dim=2)[0].min(dim=1)[0]
+    bad = int((nearest >= box_tol).sum().item())
+    assert bad <= count_slack, (bad, nearest.max().item())
 
 
 def test_dynamic_vfe_into_backbone(cuda):
@@ -545,3 +605,47 @@ def test_batched_frames_equal_single_frames(cuda):
     for k in range(2):
         for key in ('pred_boxes', 'pred_scores', 'pred_labels'):
             assert torch.equal(both[k][key], singles[k][key]), (k, key)
+
+
+def test_frame_major_schedule(cuda):
+    """batches: the schedule sorts by (frame, mask): `order` stays a permutation, its frames are contiguous and ascending, the
+    tiles are ordered frame by frame and heaviest-first inside a frame (empty capacity tiles last), and the conv output is
+    bit-identical to the unscheduled launch"""
+    from detzero_b200 import ops
+    from detzero_b200.spconv.pytorch import SparseConvTensor
+    shape, B, cin, cout = [13, 64, 64], 5, 32, 32
+    idx, f = _sparse_input(cuda, 78, B, shape, 0.05, cin)
+    t = SparseConvTensor(f.to(cuda), torch.from_numpy(idx).to(cuda), shape, B)
+    n = len(idx)
+    cap = n + 300
+    feats = torch.zeros((cap, cin), device=cuda); feats[:n] = t._feat
+    coords = torch.zeros((cap, 4), dtype=torch.int32, device=cuda); coords[:n] = t._idx
+    d_n = torch.tensor([n], dtype=torch.int32, device=cuda)
+    sws = ops.new_sched_ws(cap, cuda)
+    tab = ops.rulebook_subm(coords, d_n, cap, t.grid_index(), [3, 3, 3], layout='row', sched_ws=sws, frame_major=True)
+    order, tab_tiles = ops.rulebook_schedule(tab, d_n, sws, B, True, K=27)
+    o = order[:n].cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(n))
+    frames = idx[o, 0]
+    assert np.all(np.diff(frames) >= 0)                                       # frame-major row order
+    tiles = (cap + 127) // 128
+    to = order[cap:cap + tiles].cpu().numpy()
+    assert np.array_equal(np.sort(to), np.arange(tiles))
+    live = to[to * 128 < n]
+    assert np.array_equal(np.sort(live), np.arange((n + 127) // 128)) and np.all(to[len(live):] * 128 >= n)   # empty tiles last
+    masks = tab[:n, 27].cpu().numpy()
+    work = np.array([bin(int(np.bitwise_or.reduce(masks[o[j * 128:(j + 1) * 128]]))).count('1') for j in live])
+    tframe = frames[live * 128]
+    assert np.all(np.diff(tframe) >= 0)                                       # tiles frame by frame ...
+    for b in range(B):
+        assert np.all(np.diff(work[tframe == b]) <= 0)                        # ... heaviest-first inside a frame
+    g = np.random.default_rng(9)
+    w = torch.from_numpy(g.normal(0, 0.2, (cout, 3, 3, 3, cin)).astype(np.float32))
+    for mode in (_lib.DZ_TF32, _lib.DZ_BF16X2):
+        P = _lib.PLANES.get(mode, 0)
+        wp = ops.pack_spconv_weight(w, mode).to(cuda)
+        fin = ops.to_planes(feats, d_n, P) if P else feats
+        a = ops.spconv_fwd(fin, tab, d_n, cap, wp, None, None, None, True, mode, kshape=(27, cin, cout), layout='row')
+        b = ops.spconv_fwd(fin, tab, d_n, cap, wp, None, None, None, True, mode, kshape=(27, cin, cout), row_order=order, layout='row',
+                           tab_tiles=tab_tiles if P else None)
+        assert torch.equal(a[:n], b[:n]), mode
