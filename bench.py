@@ -1,20 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- Waymo-shape frames/sec through the B200-native DetZero detector hot path.
+"""bench.py -- Waymo-shape frames/sec through the B200-native DetZero hot path (BASELINE.json).
 
-    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W     # the reference algorithm's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W             # BASELINE configs[1] (default): this framework, one rank per GPU
+    python bench.py --impl reference --steps K --warmup W      # the reference algorithm's CPU path (oracle port), same config
+    python bench.py --config 3|4|5 ...                         # the other BASELINE configurations (see below)
 
-A "step" is one pass of the hot path over one batch of synthetic input: raw points -> hard voxelization (+MeanVFE)
--> rulebooks -> sparse VoxelBackBone8x -> BEV scatter -> BEV backbone -> CenterHead -> decode -> rotated NMS.
-Workload (BASELINE.json configs[1]): CenterPoint 1-sweep, VoxelBackBone8x, synthetic 180 K-pt Waymo-range cloud,
-fp32 storage, 8 frames per step per GPU by default (the reference's own BATCH_SIZE_PER_GPU, centerpoint_1sweep.yaml:88;
-`--batch 1` gives the single-frame latency configuration).  Frames shard across ranks with no data-path collective (weak
-scaling); see detzero_b200/dist.py for the per-sequence box gather that is NOT part of a step.
+--config 2 (default; BASELINE configs[1]): CenterPoint 1-sweep VoxelBackBone8x, synthetic 180 K-pt Waymo-range clouds, 8 frames
+    per step and GPU (the reference's BATCH_SIZE_PER_GPU, centerpoint_1sweep.yaml:88).  A step = raw points -> hard voxelization
+    (+MeanVFE) -> rulebooks -> sparse backbone -> BEV scatter -> BEV backbone -> CenterHead -> decode -> rotated NMS
+    (-> per-step NCCL all-gather of the boxes when N > 1: dist.SequenceGather, ONE collective, NMS writes into its send buffer).
+    Sparse convs default to the fp32-level `bf16x2` mode; the other modes are measured in the same run (`config.also`).
+--config 3 (BASELINE configs[2]): 5-sweep (~900 K pts) DynamicMeanVFE -> VoxelResBackBone8x in bf16 -> BEV -> head, plus the
+    sparse-conv GB/s sweep over the voxel count (`config.sweep`).
+--config 4 (BASELINE configs[3]): PRM + GRM refiner, 256 tracks x 200 boxes, 256 and 1024 points per crop; tracks/s.
+--config 5 (BASELINE configs[4]): a 199-frame sequence sharded frame i -> rank i % W, per-sequence NCCL box gather inside the
+    timed region, then PRM/GRM on tracks sharded by id and the second gather; strong scaling, frames/s.
 
-Timing: CUDA events around every step on the launching stream, L2 flushed (256 MiB write) between steps outside the
-timed intervals, max over ranks of the summed step times.  `value` has the input resident in HBM; `e2e` includes the
-pinned-host -> device copy of the step's points and the device -> host read of the boxes, through the public
-CenterPoint.forward(batch_dict) API.
+Timing: CUDA events around every step on the launching stream, L2 flushed (256 MiB write) between steps outside the timed
+intervals, max over ranks of the summed step times.  `value` has the input resident in HBM; `e2e` includes the pinned-host ->
+device copy of the step's inputs and the device -> host read of the results through the public API.
 """
 import argparse
 import json
@@ -32,6 +36,7 @@ if ROOT not in sys.path:
 
 N_POINTS = 180000
 NUM_CLOUDS = 4
+ALSO_MODES = ['tf32x3', 'tf32', 'bf16', 'bf16x2']
 
 
 def parse():
@@ -40,26 +45,29 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--backbone', default='VoxelBackBone8x', choices=['VoxelBackBone8x', 'VoxelResBackBone8x'])
+    ap.add_argument('--config', type=int, default=2, choices=[2, 3, 4, 5], help='BASELINE.json configs[config-1]')
+    ap.add_argument('--backbone', default=None, choices=['VoxelBackBone8x', 'VoxelResBackBone8x'])
     ap.add_argument('--mode', default=os.environ.get('DZ_MODE', 'tf32'),
                     help='dense BEV/head convs: tf32 (tcgen05; what the reference gets from cuDNN by default, SURVEY A.6) | fp32 (exact FMA)')
-    ap.add_argument('--sp-mode', default=os.environ.get('DZ_SP_MODE', 'tf32'),
-                    help='sparse-conv arithmetic: tf32 (tcgen05, 1 pass) | tf32x3 (tcgen05, hi/lo split) | fp32 (exact FMA, spconv default)')
-    ap.add_argument('--batch', type=int, default=8,
-                    help='frames per step and GPU; 8 = the reference config (centerpoint_1sweep.yaml:88 BATCH_SIZE_PER_GPU)')
+    ap.add_argument('--sp-mode', default=os.environ.get('DZ_SP_MODE'),
+                    help='sparse-conv arithmetic: bf16x2 (default: fp32-level, 2 bf16 planes, tcgen05) | tf32x3 (fp32-level, 3 TF32 passes) | '
+                         'fp32 (exact FMA, spconv default) | tf32 | bf16')
+    ap.add_argument('--batch', type=int, default=None,
+                    help='frames per step and GPU; config 2 default 8 = the reference config (centerpoint_1sweep.yaml:88 BATCH_SIZE_PER_GPU)')
+    ap.add_argument('--no-also', action='store_true', help='config 2: skip the extra sparse-conv modes (config.also)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-schedule', action='store_true', help='run the tensor-core sparse convs without the mask-grouped tile schedule')
-    ap.add_argument('--layer-times', action='store_true', help='print per-layer sparse-conv times of the traced frame to stderr')
-    ap.add_argument('--modules', type=int, default=0, help='diagnostic: graph-replay time of only the first N modules of the detector (stderr, then exit)')
+    ap.add_argument('--layer-times', action='store_true', help='print per-layer sparse-conv times of the traced step to stderr')
     ap.add_argument('--stage-times', action='store_true', help='print a per-stage device time table to stderr')
     return ap.parse_args()
 
 
-def make_model_cfg(backbone, mode, sp_mode):
+def make_model_cfg(backbone, mode, sp_mode, vfe='MeanVFE'):
     from detzero_b200 import synthetic
     cfg = synthetic.model_cfg(backbone, mode)
     cfg.BACKBONE_3D.COMPUTE_MODE = sp_mode
+    cfg.VFE.NAME = vfe
     if os.environ.get('DZ_NO_OVERLAP'):
         cfg.BACKBONE_3D.OVERLAP_RULEBOOKS = False      # diagnostic: rulebooks inline on the main stream
     return cfg
@@ -80,13 +88,13 @@ def tune_head_for_bench(model):
     return {k: v.detach().clone() for k, v in model.state_dict().items()}
 
 
-def build_inputs(batch):
+def build_inputs(batch, num_batches=NUM_CLOUDS, seed0=0):
     from detzero_b200 import synthetic
     from detzero_b200.det.dataset import SyntheticWaymoDataset, default_waymo_1sweep_cfg
-    ds = SyntheticWaymoDataset(default_waymo_1sweep_cfg(), synthetic.CLASS_NAMES, training=False, num_frames=NUM_CLOUDS * batch,
-                               n_points=N_POINTS)
+    ds = SyntheticWaymoDataset(default_waymo_1sweep_cfg(), synthetic.CLASS_NAMES, training=False, num_frames=num_batches * batch,
+                               n_points=N_POINTS, seed0=seed0)
     batches = []
-    for i in range(NUM_CLOUDS):
+    for i in range(num_batches):
         items = [ds[i * batch + j] for j in range(batch)]
         for it in items:                    # fixed shape for CUDA-graph replay: pad with far out-of-range points (dropped by
             p = it['points']                # the voxelizer exactly like any other out-of-range point)
@@ -125,6 +133,13 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path)), 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops_sustained': 1450.0}, 'fallback'
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference path (voxelizer C restatement + spconv 'Native' + torch-CPU convs)
 # ------------------------------------------------------------------------------------------------------------------
@@ -154,15 +169,20 @@ def cpu_frame_fn(backbone, seed=3):
     return run
 
 
+def workload_name(backbone, batch):
+    return 'CenterPoint 1-sweep %s, synthetic 180K-pt Waymo-range cloud, fp32, batch %d/GPU' % (backbone, batch)
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm on the host cores (oracle port; spconv itself cannot be installed
-    here).  One step = one frame.  Under torchrun only rank 0 works."""
+    here).  Same workload as the GPU arm; one step = one FRAME of it (a bounded sample).  Under torchrun only rank 0 works."""
     import torch
     if int(os.environ.get('RANK', '0')) != 0:
         return
+    backbone = args.backbone or 'VoxelBackBone8x'
     cores = cpu_threads()
     torch.set_num_threads(cores)
-    run = cpu_frame_fn(args.backbone)
+    run = cpu_frame_fn(backbone)
     for i in range(args.warmup):
         run(i)
     t0 = time.perf_counter()
@@ -173,261 +193,13 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'Waymo-shape frames/sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * dt / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': 'CenterPoint 1-sweep %s, synthetic 180K-pt Waymo-range cloud, fp32, batch %d/GPU'
-                                   % (args.backbone, args.batch),
-                       'arm': 'oracle port of the reference algorithm on the host CPU (spconv cannot be installed here)'},
+            'config': {'workload': workload_name(backbone, args.batch or 8),
+                       'arm': 'oracle port of the reference algorithm on the host CPU (spconv cannot be installed here); one step = ONE frame '
+                              'of the workload (bounded sample): CPU frames/s does not depend on the batch size'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d frames of the same workload, torch threads=%d' % (args.steps, cores)},
+                             'sample': '%d frames of the same workload, one frame per step, torch threads=%d' % (args.steps, cores)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
-
-
-# ------------------------------------------------------------------------------------------------------------------
-def main():
-    args = parse()
-    if args.impl == 'reference':
-        return run_reference(args)
-    import torch
-    import torch.distributed as dist
-    from detzero_b200 import ops, synthetic as weights
-    from detzero_b200.det import build_network
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm'
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-
-    ds, batches = build_inputs(args.batch)
-    if os.environ.get('DZ_SIDE_PRIO') == '0':
-        from detzero_b200.det import backbone3d as _b3
-        _b3._Backbone8xBase.SIDE_STREAM_HIGH_PRIORITY = False
-    if args.no_schedule:
-        from detzero_b200.spconv import pytorch as _sp
-        _sp._SparseConv.SCHEDULE_TILES = False
-    model = build_network(make_model_cfg(args.backbone, args.mode, args.sp_mode), 3, ds).eval()
-    weights.load_seeded(model, 3)
-    tune_head_for_bench(model)
-    model = model.to(dev)
-
-    # pinned host copies (e2e arm) and resident device copies (value arm); each rank takes its own frames
-    host_pts = [torch.from_numpy(b['points']).pin_memory() for b in batches]
-    dev_pts = [h.to(dev) for h in host_pts]
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    out_host = torch.empty((args.batch, 500, 9), dtype=torch.float32).pin_memory()
-
-    def batch_dict(i, pts):
-        b = batches[i % NUM_CLOUDS]
-        return {'points': pts, 'points_per_frame': b['points_per_frame'], 'frame_id': b['frame_id'], 'batch_size': b['batch_size']}
-
-    graph_state = {}
-    e2e_state = {'d2h': 0, 'boxes': 0}
-
-    def step_resident(i):
-        if graph_state:
-            graph_state['in'].copy_(dev_pts[i % NUM_CLOUDS], non_blocking=True)      # device->device, part of the step
-            graph_state['g'].replay()
-            return graph_state['out']
-        with torch.no_grad():
-            bd = model.forward_device(batch_dict(i, dev_pts[i % NUM_CLOUDS]))
-        return bd
-
-    def step_e2e(i):
-        with torch.no_grad():
-            if graph_state:
-                graph_state['in'].copy_(host_pts[i % NUM_CLOUDS], non_blocking=True)     # pinned host -> device
-                graph_state['g'].replay()
-                pred, _ = model.post_processing(graph_state['out'])                      # the step's D2H (counts) + dicts
-            else:
-                pts = host_pts[i % NUM_CLOUDS].to(dev, non_blocking=True)
-                pred, _ = model(batch_dict(i, pts))                   # public API: includes the D2H read of counts
-            d2h = 4 * len(pred)                                        # the count read inside post_processing
-            for b, pd in enumerate(pred):                              # every frame's boxes go back to pinned host memory
-                n = pd['pred_boxes'].shape[0]
-                out_host[b, :n, :7].copy_(pd['pred_boxes'], non_blocking=True)
-                d2h += n * 7 * 4
-            e2e_state['d2h'], e2e_state['boxes'] = d2h, sum(pd['pred_boxes'].shape[0] for pd in pred)
-        return pred
-
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        evs = []
-        ops.reset_launch_count()
-        for i in range(steps):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            fn(warmup + i)
-            e.record()
-            evs.append((s, e))
-        torch.cuda.synchronize()
-        launches = ops.launch_count() if not graph_state else graph_state.get('launches_per_step', 0) * steps
-        if world > 1:
-            dist.barrier()
-        total_ms = sum(s.elapsed_time(e) for s, e in evs)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item(), launches
-
-    # capacity hints (buffer sizes / launch grids follow the observed sparsity): a few full frames through the public API
-    for rep in range(2):
-        for i in range(NUM_CLOUDS):
-            step_e2e(i)
-    torch.cuda.synchronize()
-
-    if args.stage_times and rank == 0:
-        # main-stream device time per module of the eager frame (rulebook side streams overlap the backbone's convs)
-        names = [type(m).__name__ for m in model.module_list]
-        acc = [0.0] * len(names)
-        reps = 6
-        with torch.no_grad():
-            for f in range(reps + 2):
-                bd = batch_dict(f, dev_pts[f % NUM_CLOUDS])
-                flush.zero_()
-                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-                evs[0].record()
-                for k, m in enumerate(model.module_list):
-                    bd = m(bd)
-                    evs[k + 1].record()
-                torch.cuda.synchronize()
-                if f >= 2:
-                    for k in range(len(names)):
-                        acc[k] += evs[k].elapsed_time(evs[k + 1]) / reps
-        print('stage times (eager, us/frame): ' + ', '.join('%s %.0f' % (n, 1000 * t) for n, t in zip(names, acc)) +
-              ' | total %.0f' % (1000 * sum(acc)), file=sys.stderr)
-
-    if args.modules and rank == 0:
-        full = list(model.module_list)
-        for nmod in range(1, len(full) + 1):
-            model.module_list = full[:nmod]
-            sp = dev_pts[0].clone()
-            gg, _ = model.capture_graph(batch_dict(0, sp), warmup=1)
-            ts = []
-            for i in range(13):
-                flush.zero_()
-                sp.copy_(dev_pts[i % NUM_CLOUDS])
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); gg.replay(); e1.record()
-                torch.cuda.synchronize()
-                if i >= 3:
-                    ts.append(e0.elapsed_time(e1))
-            ts.sort()
-            print('graph replay of the first %d modules (.. %s): median %.0f us' % (nmod, type(full[nmod - 1]).__name__, 1000 * ts[len(ts) // 2]), file=sys.stderr)
-        model.module_list = full
-        return
-
-    if not args.no_graph:
-        static_pts = dev_pts[0].clone()
-        ops.reset_launch_count()
-        g, out = model.capture_graph(batch_dict(0, static_pts), warmup=0)
-        graph_state.update(g=g, out=out, launches_per_step=ops.launch_count())
-        graph_state['in'] = static_pts
-        for i in range(NUM_CLOUDS):                         # replay sanity: same detections as the eager path
-            step_resident(i)
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    total_ms, launches = timed(step_resident, args.steps, args.warmup)
-    sampler.stop_flag = True
-    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
-    with torch.no_grad():                                   # overflow check of the resident-arm configuration
-        model.post_processing(step_resident(0))
-    frames = args.steps * args.batch * world
-    value = frames / (total_ms / 1000.0)
-    e2e = frames / (e2e_ms / 1000.0)
-
-    # ---- roofline of the dominant kernel family: the sparse convolution layers, timed live with CUDA events
-    def step_eager(i):
-        with torch.no_grad():
-            return model.forward_device(batch_dict(i, dev_pts[i % NUM_CLOUDS]))
-    roof = sparse_conv_roofline(model, step_eager, args, dev)
-
-    line = {
-        'metric': 'Waymo-shape frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': ('fp32' if args.mode == 'fp32' and args.sp_mode == 'fp32' else
-                                      'fp32 storage and accumulation; products: sparse convs %s, dense BEV/head convs %s' % (args.sp_mode, args.mode)),
-        'data': 'synthetic',
-        'config': {'workload': 'CenterPoint 1-sweep %s, synthetic 180K-pt Waymo-range cloud, fp32, batch %d/GPU'
-                               % (args.backbone, args.batch),
-                   'sparse_conv_mode': args.sp_mode, 'dense_conv_mode': args.mode, 'parallelism': 'frames sharded dp%d' % world,
-                   'l2': 'flushed (256 MiB write) between steps, outside the timed intervals',
-                   'launch': 'eager' if args.no_graph else 'CUDA graph replay of CenterPoint.forward_device',
-                   'detections_last_step': int(e2e_state['boxes'])},
-        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(host_pts[0].numel() * 4),
-                'd2h_bytes_per_step': int(e2e_state['d2h'])},          # boxes of every frame + the count read, last step
-        'gpu_launches': launches,
-        'clocks': sampler.summary(),
-        'roofline': roof,
-    }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_baseline(args)
-    if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def sparse_conv_roofline(model, step_fn, args, dev):
-    """achieved = algorithmic bytes of all sparse-conv launches of one frame / their summed duration (CUDA events on
-    the launching stream); algorithmic bytes per layer = (N_in*Cin + N_out*Cout)*4 + pairs*8 + K*Cin*Cout*4
-    (+ N_out*Cout*4 with a residual) -- SURVEY.md §8d."""
-    import torch
-    from detzero_b200 import ops
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        peak, which = json.load(open(peaks_path))['hbm_gbs'], 'measured'
-    else:
-        peak, which = 6650.0, 'fallback'
-    rec = ops.enable_spconv_trace(True)
-    step_fn(0)
-    torch.cuda.synchronize()
-    ops.enable_spconv_trace(False)
-    tot_bytes, tot_ms, tot_flops = 0.0, 0.0, 0.0
-    for r in rec:
-        if r['nbr'].shape[1] == 32 and r['nbr'].shape[0] != r['K']:      # tensor-core launch: row-major table (cap, 32)
-            valid = r['nbr'][:r['n_out'], :r['K']].t() >= 0
-            if r['row_order'] is not None:
-                valid = valid[:, r['row_order'][:r['n_out']].long()]        # tile order (for the offsets/tile statistic)
-        else:
-            valid = r['nbr'][:, :r['n_out']] >= 0
-        pairs = int(valid.sum().item())
-        if args.layer_times:
-            T = (r['n_out'] + 127) // 128
-            v = torch.zeros((valid.shape[0], T * 128), dtype=torch.bool, device=valid.device)
-            v[:, :r['n_out']] = valid
-            touched = int(v.view(valid.shape[0], T, 128).any(2).sum().item())
-            print('spconv layer K=%d cin=%d cout=%d n_out=%d pairs=%d offsets/tile=%.1f scheduled=%s  %.1f us' % (
-                r['K'], r['cin'], r['cout'], r['n_out'], pairs, touched / max(T, 1), r['row_order'] is not None,
-                1000 * r['start'].elapsed_time(r['end'])), file=sys.stderr)
-        K, cin, cout = r['K'], r['cin'], r['cout']
-        b = (r['n_in'] * cin + r['n_out'] * cout) * 4 + pairs * 8 + K * cin * cout * 4 + (r['n_out'] * cout * 4 if r['residual'] else 0)
-        tot_bytes += b
-        tot_flops += 2.0 * pairs * cin * cout
-        tot_ms += r['start'].elapsed_time(r['end'])
-    achieved = tot_bytes / (tot_ms / 1000.0) / 1e9 if tot_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath) and args.sp_mode == 'tf32' and args.backbone == 'VoxelBackBone8x':
-        tj = json.load(open(tpath))              # from the committed ncu --set full captures (same launches, cold caches)
-        if args.batch == tj.get('frames_per_step'):
-            traffic = tj['sparse_conv_dram_bytes_per_step']
-        elif args.batch == 1:
-            traffic = tj['batch1']['sparse_conv_dram_bytes_per_frame']
-    return {'bound': 'hbm', 'kernel': 'k_spconv (all %d sparse-conv launches of one step)' % len(rec), 'achieved': achieved,
-            'peak': peak, 'peak_source': which, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-            'algorithmic_bytes_per_step': tot_bytes, 'algorithmic_flops_per_step': tot_flops, 'ms_per_step': tot_ms,
-            'frames_per_step': args.batch}
 
 
 def cpu_threads():
@@ -436,11 +208,11 @@ def cpu_threads():
     return max(1, min(os.cpu_count() or 1, int(os.environ.get('DZ_CPU_THREADS', '16'))))
 
 
-def cpu_baseline(args):
+def cpu_baseline(backbone):
     import torch
     cores = cpu_threads()
     torch.set_num_threads(cores)
-    run = cpu_frame_fn(args.backbone)
+    run = cpu_frame_fn(backbone)
     run(0)
     t0 = time.perf_counter()
     n = 0
@@ -450,6 +222,553 @@ def cpu_baseline(args):
     dt = time.perf_counter() - t0
     return {'value': n / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
             'sample': '%d frames of the same workload (oracle port: C voxelizer + spconv-Native restatement + torch-CPU convs)' % n}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class Env:
+    """ranks, device, timing helpers shared by the configurations"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm'
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)
+
+    def timed(self, fn, steps, warmup):
+        """W untimed + K timed steps, CUDA events per step, L2 flush between steps (outside the timed intervals), barrier +
+        synchronize on both sides, max over ranks of the summed step times (ms)"""
+        torch, dist = self.torch, self.dist
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for i in range(steps):
+            self.flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(warmup + i)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        total_ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def done(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+class Detector:
+    """one CenterPoint model + its captured CUDA graph for a fixed batch shape"""
+
+    def __init__(self, env, ds, batches, backbone, mode, sp_mode, use_graph=True, vfe='MeanVFE', gather=None, slab=None):
+        from detzero_b200 import ops, synthetic
+        from detzero_b200.det import build_network
+        torch = env.torch
+        self.env, self.batches, self.ops = env, batches, ops
+        self.model = build_network(make_model_cfg(backbone, mode, sp_mode, vfe), 3, ds).eval()
+        synthetic.load_seeded(self.model, 3)
+        tune_head_for_bench(self.model)
+        self.model = self.model.to(env.dev)
+        self.host_pts = [torch.from_numpy(b['points']).pin_memory() for b in batches]
+        self.dev_pts = [h.to(env.dev) for h in self.host_pts]
+        self.gather = gather                               # dist.SequenceGather (per-step gather) or None
+        self.slab = slab if slab is not None else (gather.slot(0, batches[0]['batch_size']) if gather is not None else None)
+        self.graph = None
+        self.launches_per_step = 0
+        self.use_graph = use_graph
+
+    def batch_dict(self, i, pts):
+        b = self.batches[i % len(self.batches)]
+        d = {'points': pts, 'points_per_frame': b['points_per_frame'], 'frame_id': b['frame_id'], 'batch_size': b['batch_size']}
+        if self.slab is not None:
+            d['gather_slab'] = self.slab                   # NMS writes straight into the gather's send buffer
+        return d
+
+    def settle(self):
+        """capacity hints (buffer sizes / launch grids follow the observed sparsity): every input through the public API until no
+        overflow is reported"""
+        torch = self.env.torch
+        for rep in range(2):
+            for i in range(len(self.batches)):
+                for attempt in range(6):
+                    try:
+                        with torch.no_grad():
+                            self.model(self.batch_dict(i, self.dev_pts[i]))
+                        break
+                    except RuntimeError as e:
+                        if 'overflow' not in str(e):
+                            raise
+        torch.cuda.synchronize()
+
+    def capture(self):
+        if not self.use_graph:
+            return
+        self.static_pts = self.dev_pts[0].clone()
+        self.ops.reset_launch_count()
+        self.graph, self.out = self.model.capture_graph(self.batch_dict(0, self.static_pts), warmup=0)
+        self.launches_per_step = self.ops.launch_count()
+
+    def step_resident(self, i):
+        torch = self.env.torch
+        k = i % len(self.batches)
+        if self.graph is not None:
+            self.static_pts.copy_(self.dev_pts[k], non_blocking=True)      # device->device, part of the step
+            self.graph.replay()
+            out = self.out
+        else:
+            with torch.no_grad():
+                out = self.model.forward_device(self.batch_dict(i, self.dev_pts[k]))
+        if self.gather is not None:
+            self.gathered = self.gather.gather()                           # ONE NCCL all-gather, inside the timed region
+        return out
+
+    def step_e2e(self, i, out_host, state):
+        torch = self.env.torch
+        k = i % len(self.batches)
+        with torch.no_grad():
+            if self.graph is not None:
+                self.static_pts.copy_(self.host_pts[k], non_blocking=True)     # pinned host -> device
+                self.graph.replay()
+                pred, _ = self.model.post_processing(self.out)                 # the step's D2H (counts, overflow flag) + dicts
+            else:
+                pts = self.host_pts[k].to(self.env.dev, non_blocking=True)
+                pred, _ = self.model(self.batch_dict(i, pts))                  # public API: includes the D2H read of counts
+            if self.gather is not None:
+                self.gathered = self.gather.gather()
+            d2h = 4 * (len(pred) + 8)                                          # the count / flag read inside post_processing
+            for b, pd in enumerate(pred):                                      # every frame's boxes go back to pinned host memory
+                n = pd['pred_boxes'].shape[0]
+                out_host[b, :n, :7].copy_(pd['pred_boxes'], non_blocking=True)
+                d2h += n * 7 * 4
+            state['d2h'], state['boxes'] = d2h, sum(pd['pred_boxes'].shape[0] for pd in pred)
+        return pred
+
+
+def sparse_conv_roofline(det, layer_times, batch, storage_bytes=4):
+    """achieved = algorithmic bytes of all sparse-conv launches of one step / their summed duration (CUDA events on the
+    launching stream, one eager traced step); algorithmic bytes per layer = (N_in*Cin + N_out*Cout)*s + pairs*8 + K*Cin*Cout*s
+    (+ N_out*Cout*s with a residual), s = storage bytes per value -- SURVEY.md §8d."""
+    import torch
+    from detzero_b200 import ops
+    peaks, which = hbm_peak()
+    peak = peaks['hbm_gbs']
+    rec = ops.enable_spconv_trace(True)
+    with torch.no_grad():
+        det.model.forward_device(det.batch_dict(0, det.dev_pts[0]))
+    torch.cuda.synchronize()
+    ops.enable_spconv_trace(False)
+    tot_bytes, tot_ms, tot_flops, layers = 0.0, 0.0, 0.0, []
+    s = storage_bytes
+    for r in rec:
+        if r['nbr'].shape[1] == 32 and r['nbr'].shape[0] != r['K']:      # tensor-core launch: row-major table (cap, 32)
+            valid = r['nbr'][:r['n_out'], :r['K']].t() >= 0
+            if r['row_order'] is not None:
+                valid = valid[:, r['row_order'][:r['n_out']].long()]        # tile order (for the offsets/tile statistic)
+        else:
+            valid = r['nbr'][:, :r['n_out']] >= 0
+        pairs = int(valid.sum().item())
+        K, cin, cout = r['K'], r['cin'], r['cout']
+        b = (r['n_in'] * cin + r['n_out'] * cout) * s + pairs * 8 + K * cin * cout * s + (r['n_out'] * cout * s if r['residual'] else 0)
+        ms = r['start'].elapsed_time(r['end'])
+        if layer_times:
+            T = (r['n_out'] + 127) // 128
+            v = torch.zeros((valid.shape[0], T * 128), dtype=torch.bool, device=valid.device)
+            v[:, :r['n_out']] = valid
+            touched = int(v.view(valid.shape[0], T, 128).any(2).sum().item())
+            print('spconv layer K=%d cin=%d cout=%d n_out=%d pairs=%d offsets/tile=%.1f scheduled=%s  %.1f us  %.0f GB/s' % (
+                K, cin, cout, r['n_out'], pairs, touched / max(T, 1), r['row_order'] is not None, 1000 * ms, b / ms / 1e6), file=sys.stderr)
+        layers.append({'K': K, 'cin': cin, 'cout': cout, 'n_out': r['n_out'], 'us': round(1000 * ms, 1), 'GBps': round(b / ms / 1e6, 1)})
+        tot_bytes += b
+        tot_flops += 2.0 * pairs * cin * cout
+        tot_ms += ms
+    achieved = tot_bytes / (tot_ms / 1000.0) / 1e9 if tot_ms > 0 else 0.0
+    return {'bound': 'hbm', 'kernel': 'sparse conv (all %d sparse-conv launches of one step)' % len(rec), 'achieved': achieved,
+            'peak': peak, 'peak_source': which, 'unit': 'GB/s', 'frac': achieved / peak,
+            'traffic': None, 'traffic_note': 'not measured in this run; the ncu --set full capture of the same launches is committed under profiles/',
+            'algorithmic_bytes_per_step': tot_bytes, 'storage_bytes_per_value': s, 'algorithmic_flops_per_step': tot_flops,
+            'ms_per_step': tot_ms, 'frames_per_step': batch, 'layers': layers}
+
+
+SP_DTYPE = {'fp32': 'fp32 FMA', 'tf32x3': 'tf32x3 (3 TF32 passes, fp32-level)',
+            'bf16x2': 'bf16x2 (2 bf16 planes = 16 significand bits in 4 bytes, fp32 accumulate; <= 2e-4 vs the fp32 oracle through the whole backbone)',
+            'tf32': 'tf32 (1 pass)', 'bf16': 'bf16 (storage and products)'}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_config2(args):
+    from detzero_b200 import synthetic
+    from detzero_b200 import dist as dzdist
+    env = Env()
+    torch = env.torch
+    backbone = args.backbone or 'VoxelBackBone8x'
+    batch = args.batch or 8
+    sp_mode = args.sp_mode or synthetic.DEFAULT_SP_MODE
+    if args.no_schedule:
+        from detzero_b200.spconv import pytorch as _sp
+        _sp._SparseConv.SCHEDULE_TILES = False
+    ds, batches = build_inputs(batch, seed0=env.rank * 64)            # each rank takes its own frames
+    gather = dzdist.SequenceGather(batch * env.world, K=500, device=env.dev) if env.world > 1 else None
+    det = Detector(env, ds, batches, backbone, args.mode, sp_mode, use_graph=not args.no_graph, gather=gather)
+    det.settle()
+    out_host = torch.empty((batch, 500, 9), dtype=torch.float32).pin_memory()
+    state = {'d2h': 0, 'boxes': 0}
+
+    if args.stage_times and env.rank == 0:
+        names = [type(m).__name__ for m in det.model.module_list]
+        acc, reps = [0.0] * len(names), 6
+        with torch.no_grad():
+            for f in range(reps + 2):
+                bd = det.batch_dict(f, det.dev_pts[f % len(batches)])
+                env.flush.zero_()
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                evs[0].record()
+                for k, m in enumerate(det.model.module_list):
+                    bd = m(bd)
+                    evs[k + 1].record()
+                torch.cuda.synchronize()
+                if f >= 2:
+                    for k in range(len(names)):
+                        acc[k] += evs[k].elapsed_time(evs[k + 1]) / reps
+        print('stage times (eager, us/step): ' + ', '.join('%s %.0f' % (n, 1000 * t) for n, t in zip(names, acc)) +
+              ' | total %.0f' % (1000 * sum(acc)), file=sys.stderr)
+
+    det.capture()
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    total_ms = env.timed(det.step_resident, args.steps, args.warmup)
+    sampler.stop_flag = True
+    e2e_ms = env.timed(lambda i: det.step_e2e(i, out_host, state), args.steps, args.warmup)
+    with torch.no_grad():                                   # overflow check of the resident-arm configuration (flag + counts)
+        det.model.post_processing(det.step_resident(0))
+    frames = args.steps * batch * env.world
+    value, e2e = frames / (total_ms / 1000.0), frames / (e2e_ms / 1000.0)
+    launches = (det.launches_per_step if det.graph is not None else 0) * args.steps
+    roof = sparse_conv_roofline(det, args.layer_times, batch, storage_bytes=2 if sp_mode == 'bf16' else 4)
+
+    also = {}
+    if not args.no_also and env.world == 1:
+        steps2 = min(args.steps, 10)
+        for m in ALSO_MODES:
+            if m == sp_mode:
+                continue
+            d2 = Detector(env, ds, batches, backbone, args.mode, m, use_graph=not args.no_graph)
+            d2.settle()
+            d2.capture()
+            ms2 = env.timed(d2.step_resident, steps2, max(2, min(args.warmup, 3)))
+            r2 = sparse_conv_roofline(d2, False, batch, storage_bytes=2 if m == 'bf16' else 4)
+            also[m] = {'value': steps2 * batch / (ms2 / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms2 / steps2, 'steps': steps2,
+                       'sparse_conv_ms_per_step': r2['ms_per_step'], 'sparse_conv_roofline_frac': r2['frac'], 'precision': SP_DTYPE[m]}
+            del d2
+            torch.cuda.empty_cache()
+
+    line = {
+        'metric': 'Waymo-shape frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': env.world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'fp32' if (args.mode == 'fp32' and sp_mode == 'fp32') else
+                 'sparse convs: %s; dense BEV/head convs: %s products, fp32 accumulate (the reference\'s cuDNN default)' % (SP_DTYPE[sp_mode], args.mode),
+        'data': 'synthetic',
+        'config': {'workload': workload_name(backbone, batch),
+                   'sparse_conv_mode': sp_mode, 'dense_conv_mode': args.mode, 'parallelism': 'frames sharded dp%d' % env.world,
+                   'collective': ('per-step all-gather of the padded boxes of all ranks (dist.SequenceGather: ONE ncclAllGather of %d B per rank, '
+                                  'NMS writes into the send buffer), inside the timed region' % (gather.send.numel() * 4)) if gather else 'none (1 GPU)',
+                   'l2': 'flushed (256 MiB write) between steps, outside the timed intervals',
+                   'launch': 'eager' if args.no_graph else 'CUDA graph replay of CenterPoint.forward_device',
+                   'detections_last_step': int(state['boxes']), 'also': also},
+        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int(det.host_pts[0].numel() * 4),
+                'd2h_bytes_per_step': int(state['d2h'])},          # boxes of every frame + the count read, last step
+        'gpu_launches': launches,
+        'clocks': sampler.summary(),
+        'roofline': roof,
+    }
+    if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(backbone)
+    if env.rank == 0:
+        print(json.dumps(line))
+    env.done()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def five_sweep_cloud(seed, n_target=900000, subsample=1.0):
+    """BASELINE configs[2]: 5 clouds with ego-motion offsets 0..2 m and time column 0, -0.1 .. -0.4"""
+    from detzero_b200.det.dataset import synth_waymo_cloud
+    parts = [synth_waymo_cloud(seed * 5 + s, n_target // 5, sweep=s, ego_shift=0.5 * s) for s in range(5)]
+    pts = np.concatenate(parts, axis=0).astype(np.float32)              # (N, 6): x y z intensity elongation time
+    if subsample < 1.0:
+        g = np.random.default_rng(seed)
+        pts = pts[g.random(pts.shape[0]) < subsample]
+    keep = (np.abs(pts[:, 0]) <= 75.2) & (np.abs(pts[:, 1]) <= 75.2)
+    return pts[keep]
+
+
+def run_config3(args):
+    """5-sweep ~900 K-pt clouds, DynamicMeanVFE -> VoxelResBackBone8x (bf16) -> BEV -> CenterHead; one frame per step"""
+    from detzero_b200 import synthetic
+    from detzero_b200.det.dataset import SyntheticWaymoDataset, default_waymo_1sweep_cfg
+    env = Env()
+    torch = env.torch
+    backbone = args.backbone or 'VoxelResBackBone8x'
+    sp_mode = args.sp_mode or 'bf16'
+    dcfg = default_waymo_1sweep_cfg()
+    dcfg.POINT_FEATURE_ENCODING.used_feature_list = ['x', 'y', 'z', 'intensity', 'elongation', 'offset']      # waymo_5sweeps.yaml: + time
+    ds = SyntheticWaymoDataset(dcfg, synthetic.CLASS_NAMES, training=False, num_frames=1, n_points=N_POINTS)
+
+    def batches_for(sub, n=NUM_CLOUDS):
+        out, npts = [], None
+        for i in range(n):
+            p = five_sweep_cloud(env.rank * 16 + i, subsample=sub)
+            npts = p.shape[0] if npts is None else npts
+            p = p[:npts] if p.shape[0] >= npts else np.concatenate([p, np.full((npts - p.shape[0], 6), 1.0e4, np.float32)])
+            out.append({'points': np.pad(p, ((0, 0), (1, 0))).astype(np.float32), 'points_per_frame': [npts], 'frame_id': np.array(['s%d' % i]),
+                        'batch_size': 1})
+        return out
+    batches = batches_for(1.0)
+    det = Detector(env, ds, batches, backbone, args.mode, sp_mode, use_graph=not args.no_graph, vfe='DynamicMeanVFE')
+    det.settle()
+    det.capture()
+    out_host = torch.empty((1, 500, 9), dtype=torch.float32).pin_memory()
+    state = {'d2h': 0, 'boxes': 0}
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    total_ms = env.timed(det.step_resident, args.steps, args.warmup)
+    sampler.stop_flag = True
+    e2e_ms = env.timed(lambda i: det.step_e2e(i, out_host, state), args.steps, args.warmup)
+    frames = args.steps * env.world
+    sb = 2 if sp_mode == 'bf16' else 4
+    roof = sparse_conv_roofline(det, args.layer_times, 1, storage_bytes=sb)
+    with torch.no_grad():
+        od = det.model.forward_device(det.batch_dict(0, det.dev_pts[0]))
+    n_vox_full = int(od['voxel_count'].item())
+    sweep = []
+    if env.rank == 0:
+        for sub in (0.04, 0.10, 0.26, 1.0):                # ~50 K .. ~400 K+ voxels by sub-sampling the points
+            bs = batches_for(sub, 2)
+            d2 = Detector(env, ds, bs, backbone, args.mode, sp_mode, use_graph=False, vfe='DynamicMeanVFE')
+            d2.settle()
+            r = sparse_conv_roofline(d2, False, 1, storage_bytes=sb)
+            with torch.no_grad():
+                o2 = d2.model.forward_device(d2.batch_dict(0, d2.dev_pts[0]))
+            sweep.append({'points': int(bs[0]['points'].shape[0]), 'voxels': int(o2['voxel_count'].item()), 'sparse_conv_ms': r['ms_per_step'],
+                          'achieved_GBps': r['achieved'], 'frac': r['frac'], 'layers': r['layers']})
+            del d2
+            torch.cuda.empty_cache()
+    roof.pop('layers', None)
+    line = {'metric': 'Waymo-shape frames/sec', 'value': frames / (total_ms / 1000.0), 'unit': 'frames/s', 'n_gpus': env.world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'sparse convs: %s; dense BEV/head convs: %s' % (SP_DTYPE[sp_mode], args.mode), 'data': 'synthetic',
+            'config': {'workload': 'CenterPoint 5-sweep concat (%d pts, %d voxels), DynamicMeanVFE -> %s, %s, batch 1/GPU'
+                                   % (batches[0]['points'].shape[0], n_vox_full, backbone, sp_mode),
+                       'sparse_conv_mode': sp_mode, 'dense_conv_mode': args.mode, 'parallelism': 'frames sharded dp%d' % env.world,
+                       'l2': 'flushed (256 MiB write) between steps, outside the timed intervals',
+                       'launch': 'eager' if args.no_graph else 'CUDA graph replay', 'sweep': sweep},
+            'e2e': {'value': frames / (e2e_ms / 1000.0), 'unit': 'frames/s', 'h2d_bytes_per_step': int(det.host_pts[0].numel() * 4),
+                    'd2h_bytes_per_step': int(state['d2h'])},
+            'gpu_launches': (det.launches_per_step if det.graph is not None else 0) * args.steps, 'clocks': sampler.summary(), 'roofline': roof}
+    if env.rank == 0:
+        print(json.dumps(line))
+    env.done()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def prm_gflop(qpts):
+    """PRM flops per track (17.65 GFLOP at 256 query pts): the query encoder (32->128->128->256 on 200 x qpts points)
+    scales with qpts, the rest does not"""
+    enc = 2.0 * 200 * (32 * 128 + 128 * 128 + 128 * 256) / 1e9
+    return 17.65 + (qpts - 256) * enc
+
+
+class Refiner:
+    """PRM (+ GRM) on a chunk of tracks; inputs of the reference's shapes"""
+
+    def __init__(self, env, mode, tracks, qpts, with_grm=True):
+        from detzero_b200 import synthetic
+        from detzero_b200.refine import GeometryTransformer, PositionTransformer
+        torch = env.torch
+        self.env, self.tracks = env, tracks
+        cfg = synthetic.prm_cfg()
+        cfg.COMPUTE_MODE = mode
+        self.prm = PositionTransformer(cfg, 32, 32).eval()
+        synthetic.load_seeded(self.prm, 4321)
+        self.prm = self.prm.to(env.dev)
+        self.grm = None
+        if with_grm:
+            cfg = synthetic.grm_cfg()
+            cfg.COMPUTE_MODE = mode
+            self.grm = GeometryTransformer(cfg, 11, 4).eval()
+            synthetic.load_seeded(self.grm, 4322)
+            self.grm = self.grm.to(env.dev)
+        self.host = []
+        for i in range(2):
+            d = synthetic.prm_inputs(100 + i + 8 * env.rank, B=tracks, qpts=qpts)
+            if with_grm:
+                d.update(synthetic.grm_inputs(200 + i + 8 * env.rank, B=tracks))
+            self.host.append({k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in d.items()})
+        self.dev_in = [{k: v.to(env.dev) for k, v in h.items()} for h in self.host]
+        self.h2d = sum(v.numel() * v.element_size() for v in self.host[0].values())
+
+    def run(self, d):
+        torch = self.env.torch
+        with torch.no_grad():
+            out = self.prm(dict(d))['batch_box_preds']
+            out2 = self.grm(dict(d))['batch_box_preds'] if self.grm is not None else None
+        return out, out2
+
+    def step_resident(self, i):
+        return self.run(self.dev_in[i % 2])
+
+    def step_e2e(self, i, host_out):
+        d = {k: v.to(self.env.dev, non_blocking=True) for k, v in self.host[i % 2].items()}
+        a, b = self.run(d)
+        host_out[0].copy_(a, non_blocking=True)
+        if b is not None:
+            host_out[1].copy_(b, non_blocking=True)
+
+
+def run_config4(args):
+    """GRM + PRM refiner: 256 tracks x 200 boxes, crops of 256 (reference) and 1024 (BASELINE) points; a step = a chunk of tracks"""
+    from detzero_b200 import ops
+    env = Env()
+    torch = env.torch
+    mode = args.mode
+    chunk = args.batch or 16
+    res = {}
+    peaks, which = hbm_peak()
+    for qpts in (1024, 256):
+        rf = Refiner(env, mode, chunk, qpts)
+        host_out = (torch.empty((chunk, 200, 7)).pin_memory(), torch.empty((chunk, 7)).pin_memory())
+        rf.step_resident(0)
+        ops.reset_launch_count()
+        rf.step_resident(1)
+        launches = ops.launch_count()
+        sampler = ClockSampler(env.local)
+        sampler.start()
+        ms = env.timed(rf.step_resident, args.steps, args.warmup)
+        sampler.stop_flag = True
+        e2e_ms = env.timed(lambda i: rf.step_e2e(i, host_out), args.steps, args.warmup)
+        tracks = args.steps * chunk * env.world
+        tps = tracks / (ms / 1000.0)
+        gflop = prm_gflop(qpts) + 5.6
+        res[qpts] = dict(tps=tps, ms=ms / args.steps, e2e=tracks / (e2e_ms / 1000.0), launches=launches * args.steps, clocks=sampler.summary(),
+                         tflops=tps * gflop / 1e3, h2d=rf.h2d, gflop=gflop)
+        del rf
+        torch.cuda.empty_cache()
+    main = res[1024]
+    peak = peaks['bf16_tflops_sustained'] * (0.5 if mode == 'tf32' else 1.0)
+    line = {'metric': 'refiner tracks/sec (GRM + PRM)', 'value': main['tps'], 'unit': 'tracks/s', 'n_gpus': env.world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': main['ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': '%s products, fp32 accumulate and storage' % mode, 'data': 'synthetic',
+            'config': {'workload': 'GRM+PRM refiner, 256 tracks x 200 boxes per sequence in chunks of %d tracks per step, 1024 pts/crop (BASELINE) '
+                                   '[also 256 pts/crop = the reference config], 48 memory pts/box, GRM 4096 x 11 memory' % chunk,
+                       'mode': mode, 'tracks_per_step': chunk, 'parallelism': 'tracks sharded dp%d' % env.world,
+                       'l2': 'flushed (256 MiB write) between steps, outside the timed intervals', 'launch': 'eager',
+                       'also': {'256 pts/crop': {'value': res[256]['tps'], 'unit': 'tracks/s', 'ms_per_step': res[256]['ms'],
+                                                 'e2e': res[256]['e2e'], 'achieved_TFLOPs': res[256]['tflops']}}},
+            'e2e': {'value': main['e2e'], 'unit': 'tracks/s', 'h2d_bytes_per_step': int(main['h2d']), 'd2h_bytes_per_step': chunk * (200 * 7 + 7) * 4},
+            'gpu_launches': main['launches'], 'clocks': main['clocks'],
+            'roofline': {'bound': 'tensor', 'kernel': 'refiner step (point-MLP encoders + MHA + FFN + heads), %.2f GFLOP/track' % main['gflop'],
+                         'achieved': main['tflops'], 'peak': peak, 'peak_source': which + (' (bf16 sustained / 2 for TF32)' if mode == 'tf32' else ''),
+                         'unit': 'TFLOP/s', 'frac': main['tflops'] / peak, 'traffic': None}}
+    if env.rank == 0:
+        print(json.dumps(line))
+    env.done()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_config5(args):
+    """Full det + refine on a 199-frame sequence: frame i -> rank i % W (reference sampler order), per-sequence NCCL box gather inside
+    the timed region, PRM/GRM on 256 tracks sharded track j -> rank j % W, second gather.  One step = one whole sequence; strong scaling."""
+    from detzero_b200 import dist as dzdist, synthetic
+    env = Env()
+    torch, dist = env.torch, env.dist
+    F, FB, TRACKS, TCHUNK = 199, 5, 256, 16
+    backbone = args.backbone or 'VoxelBackBone8x'
+    sp_mode = args.sp_mode or synthetic.DEFAULT_SP_MODE
+    mine = dzdist.shard_indices(F, env.rank, env.world)                # frames of this rank (tail wraps like the reference sampler)
+    while len(mine) % FB:
+        mine.append(mine[0])                                           # last batch padded by wrapping
+    nb = len(mine) // FB
+    ds, pool = build_inputs(FB, num_batches=4, seed0=0)               # 20 distinct clouds, cycled over the sequence
+    gather = dzdist.SequenceGather(F, K=500, device=env.dev)
+    slab = (torch.zeros((FB, 500, 9), device=env.dev), torch.zeros((FB,), dtype=torch.int32, device=env.dev))
+    det = Detector(env, ds, pool, backbone, args.mode, sp_mode, use_graph=not args.no_graph, slab=slab)
+    det.settle()
+    det.capture()
+    my_tracks = list(range(env.rank, TRACKS, env.world))
+    n_chunks = (len(my_tracks) + TCHUNK - 1) // TCHUNK
+    rf = Refiner(env, args.mode, TCHUNK, 256)
+    rf.step_resident(0)
+    refined = torch.zeros((n_chunks * TCHUNK, 200, 7), device=env.dev)
+    refined_all = torch.empty((env.world * n_chunks * TCHUNK, 200, 7), device=env.dev) if env.world > 1 else refined
+    timing = {}
+
+    def sequence(i):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        for k in range(nb):
+            det.step_resident(i * nb + k)                                # graph replay: the NMS result lands in `slab`
+            f0, f1 = k * FB, min(gather.f_local, k * FB + FB)
+            if f1 > f0:                                                  # -> this rank's rows of the sequence send buffer
+                gather.boxes[f0:f1].copy_(slab[0][:f1 - f0], non_blocking=True)
+                gather.counts[f0:f1].copy_(slab[1][:f1 - f0], non_blocking=True)
+        e[1].record()
+        boxes, counts = gather.gather()                                  # ONE collective: all boxes of the sequence on every rank (-> tracker)
+        e[2].record()
+        for c in range(n_chunks):
+            a, _ = rf.step_resident(c)
+            refined[c * TCHUNK:(c + 1) * TCHUNK].copy_(a, non_blocking=True)
+        if env.world > 1:
+            dist.all_gather_into_tensor(refined_all, refined)            # the second gather: refined boxes per track
+        e[3].record()
+        timing['ev'] = e
+        return boxes, counts
+
+    total_ms = env.timed(sequence, args.steps, max(1, args.warmup))
+    ev = timing['ev']
+    parts = {'detect_ms': ev[0].elapsed_time(ev[1]), 'box_gather_us': 1000 * ev[1].elapsed_time(ev[2]), 'refine_ms': ev[2].elapsed_time(ev[3])}
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    b, c = sequence(0)
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    line = {'metric': 'Waymo-shape frames/sec (det + gather + refine, whole sequence)', 'value': F * args.steps / (total_ms / 1000.0), 'unit': 'frames/s',
+            'n_gpus': env.world, 'steps': args.steps, 'warmup': max(1, args.warmup), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'sparse convs: %s; dense convs + refiner: %s' % (SP_DTYPE[sp_mode], args.mode), 'data': 'synthetic',
+            'config': {'workload': 'Full det+refine: 199-frame Waymo-shape sequence (180K-pt clouds, 20 distinct, cycled) sharded frame i -> rank i %% W in '
+                                   'batches of %d, ONE NCCL all-gather of the padded boxes per sequence, then PRM+GRM on %d synthetic tracks (200 boxes, '
+                                   '256 pts/crop) sharded by id + the second gather' % (FB, TRACKS),
+                       'sparse_conv_mode': sp_mode, 'dense_conv_mode': args.mode, 'parallelism': 'frames i %% %d, tracks j %% %d' % (env.world, env.world),
+                       'frames_per_rank': len(mine), 'tracks_per_rank': len(my_tracks), 'last_sequence': parts,
+                       'gathered_boxes_total': int(c.sum().item()), 'l2': 'flushed (256 MiB write) between sequences',
+                       'launch': 'CUDA graph replay per batch of %d frames; refiner eager' % FB},
+            'e2e': None, 'gpu_launches': (det.launches_per_step * nb) * args.steps, 'clocks': sampler.summary(), 'roofline': None}
+    if env.rank == 0:
+        print(json.dumps(line))
+    env.done()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return {2: run_config2, 3: run_config3, 4: run_config4, 5: run_config5}[args.config](args)
 
 
 if __name__ == '__main__':

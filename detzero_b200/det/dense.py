@@ -302,8 +302,12 @@ class CenterHead(nn.Module):
             assert post.NMS_CONFIG.NMS_TYPE == 'nms_gpu', 'only the shipped rotated NMS is built'
             mapping = self.class_id_mapping_each_head[idx]
             assert mapping == list(range(mapping[0], mapping[0] + len(mapping))), 'non-contiguous class mapping'
+            # 'gather_slab' = (boxes (B,500,9), counts (B,)) views into the send buffer of the per-sequence box gather
+            # (dist.SequenceGather.slot): the NMS writes its result straight where the collective reads it
+            slab = data_dict.get('gather_slab') if len(self.heads_list) == 1 else None
             out, d_out = ops.nms_bev(boxes, scores, labels, d_n, float(post.NMS_CONFIG.NMS_THRESH),
-                                     int(post.NMS_CONFIG.NMS_POST_MAXSIZE), label_offset=mapping[0] + 1)
+                                     int(post.NMS_CONFIG.NMS_POST_MAXSIZE), label_offset=mapping[0] + 1,
+                                     out=None if slab is None else slab[0], d_out_n=None if slab is None else slab[1])
             padded.append(out)
             counts.append(d_out)
         self.forward_ret_dict['pred_dicts'] = pred_dicts

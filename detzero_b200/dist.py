@@ -53,3 +53,38 @@ def gather_sequence_boxes(local_boxes, local_counts, num_frames, group=None):
     boxes = boxes_all.transpose(0, 1).reshape((f_local * world,) + tuple(local_boxes.shape[1:]))   # zip(*parts)
     counts = counts_all.transpose(0, 1).reshape(f_local * world)
     return boxes[:num_frames], counts[:num_frames]
+
+
+class SequenceGather:
+    """Persistent buffers for the per-sequence box gather (replaces merge_results_dist's pickle files + 2 barriers,
+    common_utils.py:119-140): every rank owns ONE flat send buffer ``[boxes (F_local, K, 9) f32 | counts (F_local,) i32]``; the
+    detector's NMS writes each batch's result straight into ``slot(k0, k1)`` (no staging copy), and ``gather()`` is ONE
+    ``all_gather_into_tensor`` of the flat buffer (NCCL over NVLink; gloo in the CPU tests), re-interleaved
+    ``parts[r][k] -> frame k*W + r`` and truncated to the sequence length like the reference."""
+
+    def __init__(self, num_frames, K=500, device='cuda', group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.num_frames, self.K = int(num_frames), int(K)
+        self.f_local = int(math.ceil(num_frames / self.world))
+        nb = self.f_local * self.K * 9
+        self.send = torch.zeros(nb + self.f_local, dtype=torch.float32, device=device)
+        self.recv = torch.empty(self.world * (nb + self.f_local), dtype=torch.float32, device=device) if self.world > 1 else self.send
+        self.boxes = self.send[:nb].view(self.f_local, self.K, 9)
+        self.counts = self.send[nb:].view(torch.int32)
+
+    def slot(self, k0, k1):
+        """(boxes (k1-k0, K, 9), counts (k1-k0,)) views for the local frames k0..k1-1 (hand them to the detector as
+        batch_dict['gather_slab'])"""
+        return self.boxes[k0:k1], self.counts[k0:k1]
+
+    def gather(self):
+        """-> (boxes (num_frames, K, 9), counts (num_frames,)) in frame order on every rank; ONE collective"""
+        if self.world == 1:
+            return self.boxes[:self.num_frames], self.counts[:self.num_frames]
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        nb = self.f_local * self.K * 9
+        parts = self.recv.view(self.world, nb + self.f_local)
+        boxes = parts[:, :nb].reshape(self.world, self.f_local, self.K, 9).transpose(0, 1).reshape(self.world * self.f_local, self.K, 9)
+        counts = parts[:, nb:].view(torch.int32).reshape(self.world, self.f_local).transpose(0, 1).reshape(-1)
+        return boxes[:self.num_frames], counts[:self.num_frames]

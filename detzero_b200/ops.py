@@ -423,12 +423,21 @@ def centerhead_decode(head, ch_layout, num_class, K, pc_range, voxel_size, fmap_
     return boxes, scores, labels, d_n
 
 
-def nms_bev(boxes, scores, labels, d_n, thresh, post_max, label_offset=1):
-    """boxes (B,cap,7) in descending score order; returns out (B,post_max,9), d_out_n (B)"""
+def nms_bev(boxes, scores, labels, d_n, thresh, post_max, label_offset=1, out=None, d_out_n=None):
+    """boxes (B,cap,7) in descending score order; returns out (B,post_max,9), d_out_n (B).  out / d_out_n may be views into a
+    caller-owned buffer -- e.g. the send buffer of the per-sequence box gather (dist.SequenceGather), so the NMS output needs
+    no staging copy before the collective"""
     B, cap, _ = boxes.shape
     dev = boxes.device
-    out = torch.empty((B, post_max, 9), dtype=torch.float32, device=dev)
-    d_out_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    if out is None:
+        out = torch.empty((B, post_max, 9), dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == (B, post_max, 9) and out.dtype == torch.float32 and out.is_contiguous()
+    if d_out_n is None:
+        d_out_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    else:
+        assert d_out_n.shape == (B,) and d_out_n.dtype == torch.int32 and d_out_n.is_contiguous()
+        d_out_n.zero_()
     ws = workspace(lib().dz_nms_bev_ws_bytes(B, cap), dev, 'nms')
     check(lib().dz_nms_bev(_p(_f32c(boxes)), _p(_f32c(scores)), _p(labels), _p(d_n), B, cap, float(thresh), post_max,
                            label_offset, _p(out), _p(d_out_n), _p(ws), ws.numel(), _stream()), 'nms_bev')

@@ -21,8 +21,14 @@ for j, f in enumerate(idx):
     boxes[j, :, 0] = f                              # tag every row with its frame id
     counts[j] = f % K + 1
 b, c = dz.gather_sequence_boxes(boxes, counts, num_frames)
+sg = dz.SequenceGather(num_frames, K=K, device='cpu')         # one flat buffer, ONE collective; producers write into slot views
+for j0 in range(0, len(idx), 2):
+    bs, cs = sg.slot(j0, min(j0 + 2, len(idx)))
+    bs.copy_(boxes[j0:j0 + 2])
+    cs.copy_(counts[j0:j0 + 2])
+b2, c2 = sg.gather()
 if rank == 0:
     with open(out, 'w') as fh:
-        json.dump({'tags': b[:, 0, 0].tolist(), 'counts': c.tolist()}, fh)
+        json.dump({'tags': b[:, 0, 0].tolist(), 'counts': c.tolist(), 'tags2': b2[:, 0, 0].tolist(), 'counts2': c2.tolist()}, fh)
 dist.barrier()
 dist.destroy_process_group()

@@ -33,3 +33,4 @@ def test_gather_world2(tmp_path):
     res = json.load(open(out))
     assert res['tags'] == [float(f) for f in range(num_frames)]          # frame order restored, truncated to length
     assert res['counts'] == [f % 4 + 1 for f in range(num_frames)]
+    assert res['tags2'] == res['tags'] and res['counts2'] == res['counts']      # SequenceGather: same order from ONE collective
