@@ -55,6 +55,12 @@ _SIGS = {
     'dz_nms_bev_ws_bytes': (sz, [ci, ci]),
     'dz_nms_bev': (ci, [vp, vp, vp, vp, ci, ci, cf, ci, ci, vp, vp, vp, sz, vp]),
     'dz_boxes_iou_bev': (ci, [vp, ci, vp, ci, vp, vp]),
+    'dz_prepare_points_ws_bytes': (sz, [ci]),
+    'dz_prepare_points': (ci, [vp, ci, vp, cf, ci, ci, vp, ci, vp, vp, sz, vp]),
+    'dz_boxes_pairwise': (ci, [vp, ci, ci, vp, ci, ci, ci, vp, vp]),
+    'dz_crop_points_ws_bytes': (sz, [ci, ci]),
+    'dz_crop_points_in_boxes': (ci, [vp, ci, ci, vp, ci, ci, vp, ci, vp, vp, sz, vp]),
+    'dz_points_in_boxes_mask': (ci, [vp, ci, ci, vp, ci, ci, vp, vp]),
     'dz_linear_fwd': (ci, [vp, ci, ci, vp, ci, vp, vp, ci, vp, ci, ci, vp]),
     'dz_group_max': (ci, [vp, ci, ci, ci, vp, vp]),
     'dz_attention_fwd': (ci, [vp, ci, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp]),

@@ -205,6 +205,34 @@ int dz_nms_bev(const float* boxes, const float* scores, const int32_t* labels, c
 /* pairwise rotated BEV IoU (iou3d_nms_kernel.cu:370-384 boxes_iou_bev_kernel) */
 int dz_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* out, dz_stream_t stream);
 
+/* ---- on-disk frame -> collated device points ---------------------------------------- */
+/* raw: a frame file as waymo_utils.py:284-302 writes it, (n, 6) f32 [x,y,z,intensity,elongation,NLZ_flag], already on the device
+ * (pinned-host -> device copy of the file bytes).  Does DatasetTemplate.merge_sweeps (dataset.py:167-196) + the collate batch
+ * column (:275-283) on the device: keep NLZ_flag == -1 in file order, tanh(intensity), xyz <- [x y z 1] @ T[:3,:].T in double
+ * (transform12_host: row-major 3x4 of inv(current_pose) @ sweep_pose, NULL = identity), append time_offset (with_time),
+ * prepend batch_idx.  Rows (1 + 5 + with_time floats) are appended at d_count[0]; d_count[1] = rows wanted (> cap: overflow). */
+size_t dz_prepare_points_ws_bytes(int n);
+int dz_prepare_points(const float* raw, int n, const double* transform12_host, float time_offset, int with_time, int batch_idx,
+                      float* out, int cap, int* d_count, void* ws, size_t ws_bytes, dz_stream_t stream);
+
+/* ---- tracker association matrices + object crop ---------------------------------- */
+/* out (na, nb) = kind(boxes_a[i], boxes_b[j]); boxes are rows of >= 7 floats [x,y,z,dx,dy,dz,heading,...] with row strides
+ * lda / ldb floats, so the matrices can be computed straight from the all-gathered (F, 500, 9) detection tensor.
+ * kind 0: rotated-BEV IoU (IoUBEV_dis_mat -> boxes_iou_bev_gpu), 1: BEV overlap area (bev_overlap_gpu, the tracker's overlap
+ * filter), 2: 3-D IoU (IoU3D_dis_mat -> boxes_iou3d_gpu, iou3d_nms_utils.py:74-107), 3: axis-aligned 2-D IoU on (x,y,dx,dy)
+ * (IoU2D_dis_mat).  Replaces tracking/detzero_track/models/tracking_modules/data_association/distance.py:44-141. */
+int dz_boxes_pairwise(const float* boxes_a, int na, int lda, const float* boxes_b, int nb, int ldb, int kind, float* out,
+                      dz_stream_t stream);
+/* Object crop: which points (rows of pt_stride >= 3 floats, x,y,z first) lie inside which box -- points_in_boxes_gpu_v2
+ * (roiaware_pool3d_kernel.cu:23-36,352-372; daemon/prepare_object_data.py:264-311) -- as the ORDERED index list the daemon builds
+ * on the host: idx (n_boxes, cap) = indices of box t's points in input order (-1 padded, first cap kept), num (n_boxes) = true
+ * counts.  dz_points_in_boxes_mask writes the reference's own (n_boxes, n_pts) int32 mask. */
+size_t dz_crop_points_ws_bytes(int n_pts, int n_boxes);
+int dz_crop_points_in_boxes(const float* points, int n_pts, int pt_stride, const float* boxes, int n_boxes, int ldb,
+                            int32_t* idx, int cap, int* num, void* ws, size_t ws_bytes, dz_stream_t stream);
+int dz_points_in_boxes_mask(const float* points, int n_pts, int pt_stride, const float* boxes, int n_boxes, int ldb,
+                            int32_t* mask, dz_stream_t stream);
+
 /* ---- refiner (GRM / PRM / CRM) ------------------------------------------------------------------------- */
 /* y = act((x @ W^T) * scale + shift): x (M,K) row-major, W (N,K) row-major (nn.Linear / 1x1 Conv layout).
  * Replaces F.linear and the Conv1d/Conv2d(k=1)+BN+ReLU MLP stacks (utils/detzero_utils/model_utils.py:81-134). */

@@ -247,3 +247,20 @@ def generate_predicted_boxes(maps, pc_range, voxel_size, fmap_stride, post_cfg, 
         out.append(dict(pred_boxes=d['pred_boxes'][sel], pred_scores=d['pred_scores'][sel],
                         pred_labels=d['pred_labels'][sel].long() + 1))
     return out
+
+
+def merge_sweeps(info, target_infos, points):
+    """DatasetTemplate.merge_sweeps (detection/detzero_det/datasets/dataset.py:167-196), statement by statement: NLZ filter, tanh of
+    the intensity, ego-motion transform through the float64 poses, time-offset column"""
+    current_pose, current_time = info['pose'], info['time_stamp']
+    clouds = []
+    for i in range(len(target_infos)):
+        cur = points[i]
+        cur, nlz = cur[:, 0:5], cur[:, 5]
+        cur = cur[nlz == -1]
+        cur[:, 3] = np.tanh(cur[:, 3])
+        T = np.linalg.inv(current_pose) @ target_infos[i]['pose']
+        dt = int(target_infos[i]['time_stamp']) - int(current_time)
+        cur[:, :3] = np.concatenate([cur[:, :3], np.ones((cur.shape[0], 1))], axis=1) @ T[:3, :].T
+        clouds.append(np.concatenate([cur, float(dt) / 1000000. * np.ones((cur.shape[0], 1))], axis=1))
+    return np.concatenate(clouds, axis=0)

@@ -188,6 +188,35 @@ void oracle_boxes_iou_bev(const float *boxes_a, int na, const float *boxes_b, in
             out[(size_t)i * nb + j] = oracle_iou_bev(boxes_a + i * 7, boxes_b + j * 7);
 }
 
+/* boxes_overlap_bev_gpu (iou3d_nms_kernel.cu:337-350): the overlap AREA matrix the tracker's overlap filter and
+ * boxes_iou3d_gpu (iou3d_nms_utils.py:74-107) are built on */
+void oracle_boxes_overlap_bev(const float *boxes_a, int na, const float *boxes_b, int nb, float *out)
+{
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j)
+            out[(size_t)i * nb + j] = oracle_box_overlap(boxes_a + i * 7, boxes_b + j * 7);
+}
+
+/* points_in_boxes_gpu_v2 (roiaware_pool3d_kernel.cu:16-36,352-372): mask[t][m] = 1 iff point m is inside box t;
+ * GPU margin 1e-5 on x/y in the box frame, none on z */
+void oracle_points_in_boxes(const float *pts, int n_pts, int pt_stride, const float *boxes, int n_boxes, int32_t *mask)
+{
+    for (int t = 0; t < n_boxes; ++t) {
+        const float *b = boxes + (size_t)t * 7;
+        float cosa = cosf(-b[6]), sina = sinf(-b[6]);
+        for (int m = 0; m < n_pts; ++m) {
+            const float *q = pts + (size_t)m * pt_stride;
+            int in = 0;
+            if (!(fabsf(q[2] - b[2]) > b[5] / 2.0f)) {
+                float sx = q[0] - b[0], sy = q[1] - b[1];
+                float lx = sx * cosa + sy * (-sina), ly = sx * sina + sy * cosa;
+                in = (fabsf(lx) < b[3] / 2.0f + 1e-5f) & (fabsf(ly) < b[4] / 2.0f + 1e-5f);
+            }
+            mask[(size_t)t * n_pts + m] = in;
+        }
+    }
+}
+
 /* NMS over boxes ALREADY sorted by descending score (iou3d_nms_utils.py:154-170 sorts, then
  * nms_kernel builds the j>i suppression mask (:386-430) and the host scans it serially
  * (iou3d_nms.cpp:139-157)).  keep[] receives indices into the sorted order; returns count. */

@@ -5,10 +5,10 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from oracle import weights
+from detzero_b200 import synthetic as weights
 from detzero_b200.det.centerpoint import build_network
 
-sp_mode = os.environ.get('DZ_SP_MODE', 'tf32')
+sp_mode = os.environ.get('DZ_SP_MODE', weights.DEFAULT_SP_MODE)
 if os.environ.get('DZ_NO_SCHEDULE'):
     from detzero_b200.spconv import pytorch as _sp
     _sp._SparseConv.SCHEDULE_TILES = False
