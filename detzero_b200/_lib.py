@@ -42,6 +42,8 @@ _SIGS = {
     'dz_rulebook_schedule_ws_bytes': (sz, [ci]),
     'dz_rulebook_schedule': (ci, [vp, ci, vp, vp, vp, sz, ci, ci, ci, vp, vp]),
     'dz_spconv_fwd': (ci, [vp, ci, ci, vp, ci, ci, vp, vp, ci, vp, vp, vp, vp, ci, vp, ci, ci, vp]),
+    'dz_rulebook_transpose': (ci, [vp, ci, ci, vp, vp, ci, vp]),
+    'dz_spconv_wgrad': (ci, [vp, ci, vp, ci, ci, vp, ci, vp, ci, vp, vp]),
     'dz_spconv_fwd_planes': (ci, [vp, ci, ci, vp, ci, ci, vp, vp, ci, vp, vp, vp, vp, ci, vp, ci, ci, vp, vp]),
     'dz_to_planes': (ci, [vp, vp, ci, ci, ci, ci, vp, vp]),
     'dz_from_planes': (ci, [vp, vp, ci, ci, ci, vp, vp]),

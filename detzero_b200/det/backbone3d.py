@@ -44,8 +44,13 @@ class SparseBasicBlock(spconv.SparseModule):
         self.stride = stride
 
     def forward(self, x):
-        if self.training:
-            raise NotImplementedError('sparse-conv backward / train-mode BN is a next row (SURVEY.md §8f rank 1)')
+        if self.training:                               # unfused, differentiable: conv -> BN (batch statistics) -> ReLU -> conv -> BN -> + x -> ReLU
+            identity = x if self.downsample is None else self.downsample(x)
+            out = self.conv1(x)
+            out = out._like(self.relu(self.bn1(out._feat)))
+            out = self.conv2(out)
+            out = out._like(self.bn2(out._feat))
+            return out._like(self.relu(out._feat + identity._feat))
         identity = x if self.downsample is None else self.downsample(x)
         s1, b1 = fold_bn(self.bn1, self.conv1.bias)
         out = self.conv1.forward_fused(x, s1, b1, None, True)
@@ -108,10 +113,10 @@ class _Backbone8xBase(nn.Module):
         x0.indice_dict['__side__'] = (side, side2)
 
     def forward(self, batch_dict):
-        if self.training:
-            raise NotImplementedError('sparse-conv backward / train-mode BN is a next row (SURVEY.md §8f rank 1)')
         x0 = self._input_tensor(batch_dict)
-        if self.model_cfg.get('OVERLAP_RULEBOOKS', True) if hasattr(self.model_cfg, 'get') else True:
+        if self.training:                               # training path: exact-size tensors, rulebooks inline (autograd)
+            pass
+        elif self.model_cfg.get('OVERLAP_RULEBOOKS', True) if hasattr(self.model_cfg, 'get') else True:
             self.prebuild_rulebooks(x0)
         x = self.conv_input(x0)
         x_conv1 = self.conv1(x)

@@ -313,6 +313,27 @@ def spconv_fwd(feats, nbr, d_n_out, out_cap, weight_packed, scale, shift, residu
     return out
 
 
+def rulebook_transpose(nbr, d_n_out, cap_in):
+    """k-major (K, cap_out) table -> (K, cap_in) table of the transposed pairs: nbrT[k][j] = o (dgrad / SparseInverseConv3d)"""
+    _need_cuda(nbr)
+    K, cap_out = nbr.shape
+    nbrT = torch.empty((K, int(cap_in)), dtype=torch.int32, device=nbr.device)
+    check(lib().dz_rulebook_transpose(_p(nbr), K, cap_out, _p(d_n_out), _p(nbrT), int(cap_in), _stream()), 'rulebook_transpose')
+    _count(2)
+    return nbrT
+
+
+def spconv_wgrad(feats, nbr, d_n_out, out_cap, dout):
+    """dW (K, cin, cout) = sum over the pairs of in[nbr[k][o]]^T (x) dout[o]; k-major table, exact fp32"""
+    _need_cuda(feats, nbr, dout)
+    K, cin, cout = nbr.shape[0], feats.shape[1], dout.shape[1]
+    dW = torch.empty((K, cin, cout), dtype=torch.float32, device=feats.device)
+    check(lib().dz_spconv_wgrad(_p(_f32c(feats)), cin, _p(nbr), K, nbr.shape[1], _p(d_n_out), out_cap, _p(_f32c(dout)), cout, _p(dW),
+                                _stream()), 'spconv_wgrad')
+    _count(1)
+    return dW
+
+
 def to_planes(x, d_n, planes, c_pad=None):
     """fp32 (rows, c) -> bf16 operand planes (rows, planes * c_pad): row = [p0 | p1], p0 = RN_bf16(x), p1 = RN_bf16(x - p0)
     (channels zero-padded to c_pad); rows >= *d_n are left untouched"""

@@ -158,6 +158,39 @@ def fold_bn(bn, conv_bias, device=None):
     return scale, shift
 
 
+class _SparseConvFn(torch.autograd.Function):
+    """training path: exact-fp32 forward on the k-major table; backward = dgrad (the forward kernel on the
+    transposed table with W^T) + wgrad (gathered A^T B per offset) + bias grad.  Tensors are exact-size here (count == capacity)."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, nbr, d_n_out, out_cap, d_n_in, kshape):
+        wp = ops.pack_spconv_weight(weight, _lib.DZ_F32)                       # (K, cin, cout)
+        out = ops.spconv_fwd(feats.contiguous(), nbr, d_n_out, out_cap, wp, None, None if bias is None else bias.detach().float(), None,
+                             False, _lib.DZ_F32, kshape=kshape, layout='k')
+        ctx.save_for_backward(feats, weight, nbr, d_n_out, d_n_in)
+        ctx.out_cap, ctx.kshape, ctx.has_bias = out_cap, kshape, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feats, weight, nbr, d_n_out, d_n_in = ctx.saved_tensors
+        K, cin, cout = ctx.kshape
+        dout = dout.contiguous().float()
+        dfeat = dweight = dbias = None
+        if ctx.needs_input_grad[0]:
+            if cin not in (16, 32, 64, 128):
+                raise NotImplementedError('dgrad for cin=%d (only the raw-voxel input layer has such a width; its input needs no gradient)' % cin)
+            nbrT = ops.rulebook_transpose(nbr, d_n_out, feats.shape[0])
+            wpT = ops.pack_spconv_weight(weight, _lib.DZ_F32).transpose(1, 2).contiguous()        # (K, cout, cin)
+            dfeat = ops.spconv_fwd(dout, nbrT, d_n_in, feats.shape[0], wpT, None, None, None, False, _lib.DZ_F32, kshape=(K, cout, cin), layout='k')
+        if ctx.needs_input_grad[1]:
+            dwp = ops.spconv_wgrad(feats.contiguous(), nbr, d_n_out, ctx.out_cap, dout)            # (K, cin, cout)
+            dweight = dwp.permute(2, 0, 1).reshape(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dbias = dout.sum(0)
+        return dfeat, dweight, dbias, None, None, None, None, None
+
+
 class _RuleSubm:
     def __init__(self, nbr, tab):
         self.nbr = nbr             # k-major table (exact-fp32 kernel) or None
@@ -248,6 +281,7 @@ class _SparseConv(SparseModule):
                 rule = _RuleConv(oc, d_n_out, out_index, (None, t) if tc else (t, None), odhw, out_cap)
             rule.sched_ws = sws
             rule.frame_major = fm
+            rule.in_idx, rule.in_count, rule.in_cap, rule.in_dhw, rule.in_index = x._idx, x._count, x._cap, x.spatial_shape, x._index
             if key is not None:
                 x.indice_dict[key] = rule
         if schedule:
@@ -306,7 +340,47 @@ class _SparseConv(SparseModule):
         t._producer = self
         return t
 
+    def _rule_train(self, x):
+        """exact-size k-major rulebook for the autograd path (one host read of the output-site count per strided conv)"""
+        key = ('train', self.indice_key)
+        rule = x.indice_dict.get(key) if self.indice_key is not None else None
+        if rule is None:
+            n_in = x.num()
+            if self.subm:
+                nbr = ops.rulebook_subm(x._idx, x._count, x._cap, x.grid_index(), self.kernel_size, layout='k')
+                rule = _RuleSubm(nbr, None)
+            else:
+                out_dhw = ops.conv_out_dhw(x.spatial_shape, self.kernel_size, self.stride, self.padding)
+                worst = 1
+                for kd, sd_ in zip(self.kernel_size, self.stride):
+                    worst *= -(-kd // sd_)
+                cells = x.batch_size * out_dhw[0] * out_dhw[1] * out_dhw[2]
+                cap = int(min(cells, max(64, n_in * worst)))
+                oc, d_n_out, out_index, nbr, odhw = ops.rulebook_conv(x._idx, x._count, x._cap, x.grid_index(), self.kernel_size, self.stride,
+                                                                      self.padding, cap, layout='k')
+                n_out = int(d_n_out.item())
+                rule = _RuleConv(oc[:n_out].contiguous(), d_n_out, out_index, (nbr[:, :n_out].contiguous(), None), odhw, n_out)
+            rule.in_idx, rule.in_count, rule.in_cap, rule.in_dhw, rule.in_index = x._idx, x._count, x._cap, x.spatial_shape, x._index
+            if self.indice_key is not None:
+                x.indice_dict[key] = rule
+        return rule
+
+    def forward_train(self, x):
+        if x._planes:
+            raise RuntimeError('the training path works on fp32 features')
+        if x._cap != x.num():
+            x = x.replace_feature(x.features)                    # exact-size tensor (count == capacity)
+            x._index = None
+        rule = self._rule_train(x)
+        if self.subm:
+            out = _SparseConvFn.apply(x._feat, self.weight, self.bias, rule.nbr, x._count, x._cap, x._count, self.kshape)
+            return x._like(out)
+        out = _SparseConvFn.apply(x._feat, self.weight, self.bias, rule.nbr, rule.d_n_out, rule.out_cap, x._count, self.kshape)
+        return SparseConvTensor(out, rule.out_idx, rule.out_dhw, x.batch_size, indice_dict=x.indice_dict, index=rule.out_index)
+
     def forward(self, x):
+        if self.training:
+            return self.forward_train(x)
         shift = None if self.bias is None else self.bias.detach().float()
         return self.forward_fused(x, None, shift, None, False)
 
@@ -325,11 +399,66 @@ class SparseConv3d(_SparseConv):
                          False, algo, kw.get('mode', 'fp32'))
 
 
+class _InverseConvFn(torch.autograd.Function):
+    """out[j] = sum over the pairs (k, j, o) of the matching SparseConv3d of W[k] in[o]: the forward kernel on the transposed table"""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, nbrT, nbr, d_n_in_sites, in_cap, d_n_out_sites, kshape):
+        wp = ops.pack_spconv_weight(weight, _lib.DZ_F32)
+        out = ops.spconv_fwd(feats.contiguous(), nbrT, d_n_in_sites, in_cap, wp, None, None if bias is None else bias.detach().float(), None,
+                             False, _lib.DZ_F32, kshape=kshape, layout='k')
+        ctx.save_for_backward(feats, weight, nbrT, nbr, d_n_in_sites, d_n_out_sites)
+        ctx.in_cap, ctx.kshape, ctx.has_bias = in_cap, kshape, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feats, weight, nbrT, nbr, d_a, d_b = ctx.saved_tensors
+        K, cin, cout = ctx.kshape
+        dout = dout.contiguous().float()
+        dfeat = dweight = dbias = None
+        if ctx.needs_input_grad[0]:
+            wpT = ops.pack_spconv_weight(weight, _lib.DZ_F32).transpose(1, 2).contiguous()
+            dfeat = ops.spconv_fwd(dout, nbr, d_b, feats.shape[0], wpT, None, None, None, False, _lib.DZ_F32, kshape=(K, cout, cin), layout='k')
+        if ctx.needs_input_grad[1]:
+            dweight = ops.spconv_wgrad(feats.contiguous(), nbrT, d_a, ctx.in_cap, dout).permute(2, 0, 1).reshape(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dbias = dout.sum(0)
+        return dfeat, dweight, dbias, None, None, None, None, None, None
+
+
 class SparseInverseConv3d(SparseModule):
-    def __init__(self, *a, **kw):
+    """spconv.SparseInverseConv3d(in, out, kernel_size, indice_key=, bias=) (post_act_block 'inverseconv', backbone3d.py:72-73):
+    undoes the sparsity pattern of the SparseConv3d that shares its ``indice_key`` -- output sites = that conv's INPUT sites,
+    ``out[j] = sum W[k] in[o]`` over that conv's pairs (k, j, o).  Exact fp32, differentiable."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key=None, bias=True, **kw):
         super().__init__()
-        raise NotImplementedError('SparseInverseConv3d is never constructed by the shipped configs '
-                                  '(backbone3d.py:72-73); listed as a next row in SURVEY.md §8f')
+        assert indice_key is not None, 'SparseInverseConv3d needs the indice_key of the SparseConv3d it inverts'
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
+        self.kernel_size = _triple(kernel_size)
+        self.indice_key = indice_key
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+
+    def forward(self, x):
+        rule = x.indice_dict.get(('train', self.indice_key)) or x.indice_dict.get(self.indice_key)
+        if rule is None or not isinstance(rule, _RuleConv):
+            raise RuntimeError('SparseInverseConv3d(%r): no SparseConv3d with this indice_key has run on this tensor' % self.indice_key)
+        K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        if rule.nbr is None:                                    # rulebook built for a tensor-core layer: k-major copy of the row-major table
+            rule.nbr = rule.tab[:, :K].t().contiguous()
+        if not hasattr(rule, 'in_idx'):
+            raise RuntimeError('rulebook %r does not remember its input sites' % self.indice_key)
+        if x._planes:
+            x = x.replace_feature(x.features)
+        if getattr(rule, 'nbrT', None) is None:
+            rule.nbrT = ops.rulebook_transpose(rule.nbr, rule.d_n_out, rule.in_cap)
+        out = _InverseConvFn.apply(x._feat, self.weight, self.bias, rule.nbrT, rule.nbr, rule.in_count, rule.in_cap, rule.d_n_out,
+                                   (K, self.in_channels, self.out_channels))
+        return SparseConvTensor(out, rule.in_idx, rule.in_dhw, x.batch_size, indice_dict=x.indice_dict, count=rule.in_count, n_host=None,
+                                index=rule.in_index)
 
 
 class SparseSequential(SparseModule):
@@ -354,7 +483,7 @@ class SparseSequential(SparseModule):
                 x = m.forward_fused(x, scale, shift, None, relu)
                 i += 3 if relu else 2
             elif isinstance(m, SparseModule):
-                x = m(x)
+                x = m(x)                       # training: _SparseConv.forward -> the autograd path, BatchNorm1d / ReLU follow unfused
                 i += 1
             else:
                 if x._planes:

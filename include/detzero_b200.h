@@ -146,6 +146,15 @@ int dz_spconv_fwd(const float* in, int cin, int in_rows, const int32_t* nbr, int
                   int out_cap, const float* weight, const float* scale, const float* shift,
                   const float* residual, int relu, float* out, int cout, int mode, dz_stream_t stream);
 
+/* Backward of dz_spconv_fwd on the same k-major table (exact fp32; the reference trains through spconv's
+ * autograd, detection/tools/train_utils.py:59-68).  dz_rulebook_transpose: nbrT (K, cap_in), nbrT[k][j] = o for every pair
+ * (k, j = nbr[k][o], o), -1 elsewhere.  dgrad = dz_spconv_fwd(d_out, nbrT, weight^T (K, cout, cin)); the transposed table with its own
+ * weights is SparseInverseConv3d (backbone3d.py:72-73).  dz_spconv_wgrad: dW (K, cin, cout) = sum_o in[nbr[k][o]]^T (x) d_out[o]. */
+int dz_rulebook_transpose(const int32_t* nbr, int K, int cap_out, const int* d_n_out, int32_t* nbrT, int cap_in,
+                          dz_stream_t stream);
+int dz_spconv_wgrad(const float* in, int cin, const int32_t* nbr, int K, int nbr_cap, const int* d_n_out, int out_cap,
+                    const float* dout, int cout, float* dW, dz_stream_t stream);
+
 /* The same layer on bf16 operand PLANES (modes DZ_BF16: planes = 1, DZ_BF16X2: planes = 2), csrc/spconv_bf16.cu: a persistent
  * warp-specialised tcgen05 kernel.  Feature tensors `in`, `residual`, `out` are (rows, planes * C) bf16, a row = [p0 | p1] with
  * x ~ p0 (+ p1), p0 = RN_bf16(x), p1 = RN_bf16(x - p0); cin <= 8 is stored padded to 8 channels per plane.  weight: (planes * cout,
