@@ -121,10 +121,40 @@ __global__ void k_group_max(const float* __restrict__ x, int G, int group, int C
     y[t] = m;
 }
 
+// few groups x many rows (PRM memory encoder: 16 tracks x 9600 keys; GRM: 4096 points): the one-thread-per-(group, channel) kernel
+// above runs on G*C/256 CTAs (16!) and took 2.1 ms of an 8 ms refiner step.  Split every group's rows over many CTAs; the max is
+// order-independent, so an atomic max (sign-aware integer compare of the float bits, y pre-set to -inf) gives the identical result.
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__global__ void k_fill_f32(float* __restrict__ y, long long n, float v) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < n) y[t] = v;
+}
+static constexpr int GM_ROWS = 64;
+__global__ void __launch_bounds__(256) k_group_max_split(const float* __restrict__ x, int group, int C, float* __restrict__ y) {
+    const int g = blockIdx.y, r0 = blockIdx.x * GM_ROWS, r1 = min(group, r0 + GM_ROWS);
+    const float* p = x + ((size_t)g * group + r0) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float m = -INFINITY;
+        for (int r = 0; r < r1 - r0; ++r) m = fmaxf(m, __ldg(p + (size_t)r * C + c));
+        atomic_max_float(y + (size_t)g * C + c, m);
+    }
+}
+
 extern "C" int dz_group_max(const float* x, int G, int group, int C, float* y, dz_stream_t stream) {
     DZ_CHECK_ARG(x && y && G >= 0 && group >= 1 && C >= 1);
     if (G == 0) return DZ_OK;
-    k_group_max<<<dz_cdiv((long long)G * C, 256), 256, 0, (cudaStream_t)stream>>>(x, G, group, C, y);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((long long)G * C < 148LL * 256 * 2 && group >= 4 * GM_ROWS) {
+        const long long n = (long long)G * C;
+        k_fill_f32<<<dz_cdiv(n, 256), 256, 0, st>>>(y, n, -INFINITY);
+        dim3 grid(dz_cdiv(group, GM_ROWS), G);
+        k_group_max_split<<<grid, C >= 256 ? 256 : 128, 0, st>>>(x, group, C, y);
+    } else {
+        k_group_max<<<dz_cdiv((long long)G * C, 256), 256, 0, st>>>(x, G, group, C, y);
+    }
     DZ_LAUNCH_CHECK();
     return DZ_OK;
 }
