@@ -155,7 +155,36 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             float* orow = p.out + (((size_t)b * p.OH + (y * p.os + p.oy0)) * p.OW + (x * p.os + p.ox0)) * p.out_cstride + p.out_coff;
             float v[32];
             tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mc, v);
-            if (p.tma_store) {
+            if (p.gmax) {
+                // fused max-pool over the points of a crop (torch.max(dim=points), position_transformer.py:109,118): the 128 rows of this
+                // tile belong to ONE group (gmax_rows % 128 == 0); warp-shuffle max over its 32 rows per column, one atomic per warp and
+                // column.  The (rows, cout) activation is never written to HBM, the group_max pass never reads it back.
+                const int grp = (p.grow0 + (ty0 + m * CT_TH) * p.Wo + tx0) / p.gmax_rows;
+                // transpose through the (idle) pipeline buffers: row stride 33 floats => conflict-free scalar stores and column reads
+                float* stg = reinterpret_cast<float*>(smem + ((mc / 32) * 4 + q) * 4352);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c0 + j;
+                    float o = v[j];
+                    if (n < p.cout) {
+                        if (p.scale) o *= __ldg(p.scale + n);
+                        if (p.shift) o += __ldg(p.shift + n);
+                        if (p.relu) o = fmaxf(o, 0.f);
+                    }
+                    stg[lane * 33 + j] = valid ? o : -INFINITY;
+                }
+                __syncwarp();
+                float cm = -INFINITY;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) cm = fmaxf(cm, stg[r * 33 + lane]);      // lane = column
+                const int n = n0 + c0 + lane;
+                if (n < p.cout) {
+                    float* addr = p.gmax + (size_t)grp * p.cout + n;
+                    if (cm >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(cm));
+                    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(cm));
+                }
+                __syncwarp();
+            } else if (p.tma_store) {
                 // The strided per-pixel stores of the direct path (32 lanes -> 32 different lines per instruction) made the
                 // epilogue as long as the main loop.  Here the warp's 32 pixels x 32 channels go to the (now idle) pipeline
                 // buffers in the 128B-swizzled box layout and ONE TMA store per warp writes them (edge tiles clipped by the
@@ -169,6 +198,10 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     if (n < p.cout) {
                         if (p.scale) { float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n)); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
                         if (p.shift) { float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n)); o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w; }
+                        if (p.gshift && valid) {
+                            float4 sh = __ldg(reinterpret_cast<const float4*>(p.gshift + (size_t)((p.grow0 + y * p.Wo + x) / p.gsize) * p.cout + n));
+                            o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w;
+                        }
                     }
                     if (p.relu) {
                         o.x = tc::rna_tf32(fmaxf(o.x, 0.f)); o.y = tc::rna_tf32(fmaxf(o.y, 0.f));
@@ -191,6 +224,10 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     if (p.scale) { float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n)); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
                     if (p.shift) { float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n)); o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w; }
+                    if (p.gshift) {
+                        float4 sh = __ldg(reinterpret_cast<const float4*>(p.gshift + (size_t)((p.grow0 + y * p.Wo + x) / p.gsize) * p.cout + n));
+                        o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w;
+                    }
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     if (p.relu) { o.x = tc::rna_tf32(o.x); o.y = tc::rna_tf32(o.y); o.z = tc::rna_tf32(o.z); o.w = tc::rna_tf32(o.w); }  // feeds another TF32 conv
                     *reinterpret_cast<float4*>(orow + n) = o;
@@ -257,7 +294,7 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
     }
     CUtensorMap tmO = tmB;
     static const int no_tma_store = getenv("DZ_CONV2D_NO_TMA_STORE") ? 1 : 0;
-    p.tma_store = (!no_tma_store && p.os == 1 && p.oy0 == 0 && p.ox0 == 0 && p.OH == p.Ho && p.OW == p.Wo && bn >= 32 &&
+    p.tma_store = (!p.gmax && !no_tma_store && p.os == 1 && p.oy0 == 0 && p.ox0 == 0 && p.OH == p.Ho && p.OW == p.Wo && bn >= 32 &&
                    (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
     if (p.tma_store) {
         // channels [0, out_coff + cout) of the (possibly wider, concatenated) output tensor: stores past cout are clipped
@@ -292,17 +329,29 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
 // F.linear / Conv1d(k=1) / Conv2d(k=1) of the refiner (utils/detzero_utils/model_utils.py:81-134) unchanged.
 // Requirements: K % 32 == 0, N % 4 == 0, ldy % 4 == 0; the M % 16 tail rows go through the exact-fp32 kernel.
 int dz_linear_fwd_f32_rows(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
-                           float* y, int ldy, cudaStream_t st);
+                           float* y, int ldy, const float* gshift, int gsize, int grow0, cudaStream_t st);
+
+// fused Linear(+BN+ReLU) + max over groups of `group` rows -> gmax (M/group, N), pre-set to -inf by the caller.  Needs the TMA shapes
+// (K % 32 == 0, N % 4 == 0) and group % 128 == 0 (a 128-row tile never straddles two groups); returns DZ_ERR_UNSUPPORTED otherwise.
+int dz_linear_max_fwd_tc(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu, int group,
+                         float* gmax, cudaStream_t st) {
+    if (K % 32 != 0 || N % 4 != 0 || group % 128 != 0 || M % group != 0) { dz_set_error("dz_linear_max_fwd: shape not supported by the fused path"); return DZ_ERR_UNSUPPORTED; }
+    const int H = M / 16;
+    Conv2dParams p{x, w, scale, shift, gmax, 1, H, 16, K, K, 1, 1, 1, 0, H, 16, N, H, 16, 1, 0, 0, 0, N, relu};
+    p.gmax = gmax; p.gmax_rows = group; p.grow0 = 0; p.gsize = 1;
+    return dz_conv2d_fwd_tc(p, DZ_TF32, st);
+}
 
 int dz_linear_fwd_tc(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu, float* y,
-                     int ldy, int mode, cudaStream_t st) {
+                     int ldy, int mode, const float* gshift, int gsize, cudaStream_t st) {
     if (mode != DZ_TF32) { dz_set_error("dz_linear_fwd: tensor-core mode %d not built (tf32 only)", mode); return DZ_ERR_UNSUPPORTED; }
     if (K % 32 != 0 || N % 4 != 0 || ldy % 4 != 0 || M < 16)      // shapes the TMA path cannot express: exact-fp32 kernel (more precise)
-        return dz_linear_fwd_f32_rows(x, M, K, w, N, scale, shift, relu, y, ldy, st);
+        return dz_linear_fwd_f32_rows(x, M, K, w, N, scale, shift, relu, y, ldy, gshift, gsize, 0, st);
     const int H = M / 16, tail = M - H * 16;
     Conv2dParams p{x, w, scale, shift, y, 1, H, 16, K, K, 1, 1, 1, 0, H, 16, N, H, 16, 1, 0, 0, 0, ldy, relu};
+    p.gshift = gshift; p.gsize = gsize > 0 ? gsize : 1; p.grow0 = 0;
     int rc = dz_conv2d_fwd_tc(p, DZ_TF32, st);
     if (rc) return rc;
-    if (tail) return dz_linear_fwd_f32_rows(x + (size_t)H * 16 * K, tail, K, w, N, scale, shift, relu, y + (size_t)H * 16 * ldy, ldy, st);
+    if (tail) return dz_linear_fwd_f32_rows(x + (size_t)H * 16 * K, tail, K, w, N, scale, shift, relu, y + (size_t)H * 16 * ldy, ldy, gshift, gsize, H * 16, st);
     return DZ_OK;
 }

@@ -18,7 +18,7 @@ static constexpr int LN_BM = 128, LN_BN = 64, LN_BK = 8, LN_THREADS = 256;
 
 __global__ void __launch_bounds__(LN_THREADS) k_linear_f32(const float* __restrict__ x, int M, int K, const float* __restrict__ w, int N,
                                                            const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                                                           float* __restrict__ y, int ldy) {
+                                                           float* __restrict__ y, int ldy, const float* __restrict__ gshift, int gsize, int grow0) {
     __shared__ __align__(16) float As[LN_BK][LN_BM + 4];
     __shared__ __align__(16) float Bs[LN_BK][LN_BN + 4];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;     // thread tile 8 rows x 4 cols
@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(LN_THREADS) k_linear_f32(const float* __restri
             float v = acc[i][j];
             if (scale) v *= __ldg(scale + n);
             if (shift) v += __ldg(shift + n);
+            if (gshift) v += __ldg(gshift + (size_t)((grow0 + m) / gsize) * N + n);
             if (relu) v = fmaxf(v, 0.f);
             y[(size_t)m * ldy + n] = v;
         }
@@ -88,26 +89,48 @@ __global__ void __launch_bounds__(LN_THREADS) k_linear_f32(const float* __restri
 }
 
 int dz_linear_fwd_tc(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
-                     float* y, int ldy, int mode, cudaStream_t st);
+                     float* y, int ldy, int mode, const float* gshift, int gsize, cudaStream_t st);
 
 int dz_linear_fwd_f32_rows(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
-                           float* y, int ldy, cudaStream_t st) {
+                           float* y, int ldy, const float* gshift, int gsize, int grow0, cudaStream_t st) {
     if (M <= 0) return DZ_OK;
     dim3 grid(dz_cdiv(M, LN_BM), dz_cdiv(N, LN_BN));
-    k_linear_f32<<<grid, LN_THREADS, 0, st>>>(x, M, K, w, N, scale, shift, relu, y, ldy);
+    k_linear_f32<<<grid, LN_THREADS, 0, st>>>(x, M, K, w, N, scale, shift, relu, y, ldy, gshift, gsize > 0 ? gsize : 1, grow0);
     DZ_LAUNCH_CHECK();
     return DZ_OK;
 }
 
+// y[m] = act((x[m] W^T) * scale + shift + gshift[m / gsize]): a linear layer whose input is the concatenation [per-group global
+// feature | per-row feature] (the PointNet "concat the max-pooled feature back" step, position_transformer.py:118-123,
+// geometry_transformer.py:131-136, confidence_pointnet.py:88-100) without materialising the concatenation: the global half of the
+// weight is applied once per GROUP (a tiny GEMM the caller runs first -> gshift (M/gsize, N), already scaled), the per-row half here.
+extern "C" int dz_linear_fwd_grouped(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift,
+                                     const float* gshift, int gsize, int relu, float* y, int ldy, int mode, dz_stream_t stream) {
+    DZ_CHECK_ARG(x && w && y && M >= 0 && K >= 1 && N >= 1 && ldy >= N && (!gshift || gsize >= 1));
+    if (M == 0) return DZ_OK;
+    if (mode != DZ_F32) return dz_linear_fwd_tc(x, M, K, w, N, scale, shift, relu, y, ldy, mode, gshift, gsize, (cudaStream_t)stream);
+    return dz_linear_fwd_f32_rows(x, M, K, w, N, scale, shift, relu, y, ldy, gshift, gsize, 0, (cudaStream_t)stream);
+}
+
+int dz_linear_max_fwd_tc(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu, int group,
+                         float* gmax, cudaStream_t st);
+__global__ void k_fill_f32(float* __restrict__ y, long long n, float v);
+
+// y (M/group, N) = max over each group of `group` consecutive rows of act((x W^T) * scale + shift): the last layer of a PointNet encoder
+// fused with torch.max over the points (model_utils.py:81-134 + position_transformer.py:109,118): the (M, N) activation never touches HBM
+extern "C" int dz_linear_max_fwd(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
+                                 int group, float* y, int mode, dz_stream_t stream) {
+    DZ_CHECK_ARG(x && w && y && M >= 1 && K >= 1 && N >= 1 && group >= 1 && M % group == 0);
+    if (mode != DZ_TF32) { dz_set_error("dz_linear_max_fwd: tensor-core mode only (the exact-fp32 path runs dz_linear_fwd + dz_group_max)"); return DZ_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)(M / group) * N;
+    k_fill_f32<<<dz_cdiv(n, 256), 256, 0, st>>>(y, n, -INFINITY);
+    return dz_linear_max_fwd_tc(x, M, K, w, N, scale, shift, relu, group, y, st);
+}
+
 extern "C" int dz_linear_fwd(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift,
                              int relu, float* y, int ldy, int mode, dz_stream_t stream) {
-    DZ_CHECK_ARG(x && w && y && M >= 0 && K >= 1 && N >= 1 && ldy >= N);
-    if (M == 0) return DZ_OK;
-    if (mode != DZ_F32) return dz_linear_fwd_tc(x, M, K, w, N, scale, shift, relu, y, ldy, mode, (cudaStream_t)stream);
-    dim3 grid(dz_cdiv(M, LN_BM), dz_cdiv(N, LN_BN));
-    k_linear_f32<<<grid, LN_THREADS, 0, (cudaStream_t)stream>>>(x, M, K, w, N, scale, shift, relu, y, ldy);
-    DZ_LAUNCH_CHECK();
-    return DZ_OK;
+    return dz_linear_fwd_grouped(x, M, K, w, N, scale, shift, nullptr, 0, relu, y, ldy, mode, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -491,6 +491,32 @@ def linear(x, w, scale=None, shift=None, relu=False, out=None, mode=_lib.DZ_F32)
     return out
 
 
+def linear_grouped(x, w, gshift, gsize, scale=None, shift=None, relu=False, mode=_lib.DZ_F32):
+    """y[m] = act((x[m] @ w.T) * scale + shift + gshift[m // gsize]); gshift (M // gsize, N) -- the fused form of
+    Linear(cat([global.expand, x])) (see dz_linear_fwd_grouped)"""
+    _need_cuda(x, w, gshift)
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and gshift.shape == (M // gsize, N) and M % gsize == 0
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(lib().dz_linear_fwd_grouped(_p(_f32c(x)), M, K, _p(_f32c(w)), N, _p(scale), _p(shift), _p(_f32c(gshift)), int(gsize), int(relu),
+                                      _p(out), N, mode, _stream()), 'linear_fwd_grouped')
+    _count(1)
+    return out
+
+
+def linear_max(x, w, group, scale=None, shift=None, relu=False, mode=_lib.DZ_TF32):
+    """max over groups of `group` rows of act((x @ w.T) * scale + shift) -> (M // group, N); see dz_linear_max_fwd"""
+    _need_cuda(x, w)
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M // group, N), dtype=torch.float32, device=x.device)
+    check(lib().dz_linear_max_fwd(_p(_f32c(x)), M, K, _p(_f32c(w)), N, _p(scale), _p(shift), int(relu), int(group), _p(y), mode, _stream()),
+          'linear_max_fwd')
+    _count(2)
+    return y
+
+
 def group_max(x, G, group):
     C = x.shape[1]
     assert x.shape[0] == G * group

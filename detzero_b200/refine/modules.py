@@ -70,11 +70,52 @@ def _w2d(m, mode=_lib.DZ_F32):
     return w2
 
 
-def run_mlp(seq, x, mode, upto=None, taps=None):
-    """token-major execution of a [Linear|Conv1x1] [BN] [ReLU] ... stack.  ``taps``: dict index -> output captured after
-    module ``index`` (the reference's register_forward_hook on ``encoder[5]``)."""
+def _first_group(mods, i=0):
+    m = mods[i]
+    assert isinstance(m, (nn.Linear, nn.Conv1d, nn.Conv2d)), type(m)
+    bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], (nn.BatchNorm1d, nn.BatchNorm2d)) else None
+    j = i + (2 if bn is not None else 1)
+    relu = j < len(mods) and isinstance(mods[j], nn.ReLU)
+    return m, bn, relu, j + (1 if relu else 0)
+
+
+def run_mlp_concat(seq, glob, per, gsize, mode, glob_first=True, pool=None):
+    """``run_mlp(seq, cat([glob.expand over each group of gsize rows, per]))`` WITHOUT materialising the concatenation
+    (position_transformer.py:118-123, geometry_transformer.py:131-136, confidence_pointnet.py:88-100 build it with expand + cat):
+    the first layer's weight is split W = [W_g | W_p]; the global half is applied once per group (a tiny GEMM) and enters
+    the per-row GEMM as a per-group shift (dz_linear_fwd_grouped).  glob (G, Cg), per (G*gsize, Cp)."""
     mods = list(seq.children())
-    i = 0
+    m, bn, relu, nxt = _first_group(mods)
+    scale, shift = fold_bn(bn, m.bias) if bn is not None else (None, (None if m.bias is None else m.bias.detach().float()))
+    Cg, Cp = glob.shape[1], per.shape[1]
+    key = (mode, Cg, Cp, glob_first)
+    cache = m.__dict__.setdefault('_dz_w2d_split', {})
+    w = m.weight
+    ver = (w._version, w.data_ptr(), w.device)
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        w32 = w.detach().reshape(w.shape[0], -1).float()
+        assert w32.shape[1] == Cg + Cp
+        wg, wp = (w32[:, :Cg], w32[:, Cg:]) if glob_first else (w32[:, Cp:], w32[:, :Cp])
+        wg, wp = wg.contiguous(), wp.contiguous()
+        if mode == _lib.DZ_TF32:
+            wg, wp = ops.round_tf32(wg), ops.round_tf32(wp)
+        hit = (ver, wg, wp)
+        cache[key] = hit
+    gshift = ops.linear(glob.contiguous(), hit[1], scale, None, False, mode=mode)                 # (G, N): (g W_g^T) * scale
+    x = ops.linear_grouped(per.contiguous(), hit[2], gshift, gsize, scale, shift, relu, mode=mode)
+    if pool and nxt >= len(mods):
+        return ops.group_max(x, x.shape[0] // pool, pool)
+    return run_mlp(seq, x, mode, start=nxt, pool=pool)
+
+
+def run_mlp(seq, x, mode, upto=None, taps=None, start=0, pool=None):
+    """token-major execution of a [Linear|Conv1x1] [BN] [ReLU] ... stack.  ``taps``: dict index -> output captured after
+    module ``index`` (the reference's register_forward_hook on ``encoder[5]``).  ``pool = group``: the stack is followed by a max over
+    groups of ``group`` consecutive rows (torch.max over a crop's points); in tensor-core mode the LAST layer and the pooling run as
+    one kernel (dz_linear_max_fwd) and the (rows, C) activation is never written."""
+    mods = list(seq.children())
+    i = start
     while i < len(mods) and (upto is None or i < upto):
         m = mods[i]
         assert isinstance(m, (nn.Linear, nn.Conv1d, nn.Conv2d)), type(m)
@@ -85,10 +126,17 @@ def run_mlp(seq, x, mode, upto=None, taps=None):
             scale, shift = fold_bn(bn, m.bias)
         else:
             scale, shift = None, (None if m.bias is None else m.bias.detach().float())
-        x = ops.linear(x, _w2d(m, mode), scale, shift, relu, mode=mode)
         i = j + (1 if relu else 0)
+        last = i >= len(mods) or (upto is not None and i >= upto)
+        K = x.shape[1]
+        if pool and last and mode == _lib.DZ_TF32 and pool % 128 == 0 and K % 32 == 0 and m.weight.shape[0] % 4 == 0 and x.shape[0] % pool == 0 \
+                and not (taps is not None and (i - 1) in taps):
+            return ops.linear_max(x, _w2d(m, mode), pool, scale, shift, relu, mode=mode)
+        x = ops.linear(x, _w2d(m, mode), scale, shift, relu, mode=mode)
         if taps is not None and (i - 1) in taps:
             taps[i - 1] = x
+    if pool:
+        x = ops.group_max(x, x.shape[0] // pool, pool)
     return x
 
 
@@ -343,15 +391,12 @@ class PositionTransformer(nn.Module):
         Pm = glob.shape[2]
         mode = self.mode
         # query: per-point MLP -> max over the crop's points -> per-box MLP
-        q = run_mlp(self.query_encoder, local.reshape(B * L * P, C).contiguous().float(), mode)
-        q = ops.group_max(q, B * L, P)
+        q = run_mlp(self.query_encoder, local.reshape(B * L * P, C).contiguous().float(), mode, pool=P)      # (B*L, E): MLP + max over the crop
         q = run_mlp(self.query_mlp, q, mode)                                             # (B*L, E)
         # memory: per-point MLP, global max over the track, concat [global, 128-ch intermediate] -> MLP
         taps = {5: None}
-        m = run_mlp(self.memory_encoder, glob.reshape(B * L * Pm, C).contiguous().float(), mode, taps=taps)
-        g = ops.group_max(m, B, L * Pm)                                                  # (B, E)
-        cat = torch.cat([g.view(B, 1, -1).expand(B, L * Pm, g.shape[1]), taps[5].view(B, L * Pm, -1)], dim=2)
-        mem = run_mlp(self.memory_mlp, cat.reshape(B * L * Pm, -1).contiguous(), mode)   # (B*L*Pm, E)
+        g = run_mlp(self.memory_encoder, glob.reshape(B * L * Pm, C).contiguous().float(), mode, taps=taps, pool=L * Pm)     # (B, E)
+        mem = run_mlp_concat(self.memory_mlp, g, taps[5], L * Pm, mode, glob_first=True)  # Linear(cat([global, 128-ch tap])) fused: (B*L*Pm, E)
         E = mem.shape[1]
         query_pos = torch.cat([traj[..., :3], traj[..., 6:]], dim=-1).float()
         data_dict['query'] = q.view(B, L, E).permute(0, 2, 1)                            # reference-shaped views (B,E,L)
@@ -396,14 +441,11 @@ class GeometryTransformer(nn.Module):
         B, N, C = mpts.shape
         mode = self.mode
         taps = {5: None}
-        m = run_mlp(self.memory_encoder, mpts.reshape(B * N, C).contiguous(), mode, taps=taps)
-        g = ops.group_max(m, B, N)
-        cat = torch.cat([taps[5].view(B, N, -1), g.view(B, 1, -1).expand(B, N, g.shape[1])], dim=2)    # [intermediate, global]
-        mem = run_mlp(self.memory_mlp, cat.reshape(B * N, -1).contiguous(), mode)
+        g = run_mlp(self.memory_encoder, mpts.reshape(B * N, C).contiguous(), mode, taps=taps, pool=N)
+        mem = run_mlp_concat(self.memory_mlp, g, taps[5], N, mode, glob_first=False)                     # cat order: [intermediate, global]
         qpts = data_dict['geo_query_points'].float()
         _, Q, P, Cq = qpts.shape
-        q = run_mlp(self.query_encoder, qpts.reshape(B * Q * P, Cq).contiguous(), mode)
-        q = ops.group_max(q, B * Q, P)
+        q = run_mlp(self.query_encoder, qpts.reshape(B * Q * P, Cq).contiguous(), mode, pool=P)
         q = run_mlp(self.query_mlp, q, mode)
         E = q.shape[1]
         qpos = data_dict['geo_query_boxes'][..., 3:6].float().contiguous()
@@ -450,16 +492,12 @@ class ConfidencePointnet(nn.Module):
         B, L, P, C = pts.shape
         mode = self.mode
         taps = {5: None}
-        f = run_mlp(self.pts_encoder_1, pts.reshape(B * L * P, C).contiguous(), mode, taps=taps)
-        g = ops.group_max(f, B * L, P)                                                   # (B*L, E)
-        cat = torch.cat([g.view(B * L, 1, -1).expand(B * L, P, g.shape[1]), taps[5].view(B * L, P, -1)], dim=2)
-        f = run_mlp(self.pts_encoder_2, cat.reshape(B * L * P, -1).contiguous(), mode)
-        pool = ops.group_max(f, B * L, P)
+        g = run_mlp(self.pts_encoder_1, pts.reshape(B * L * P, C).contiguous(), mode, taps=taps, pool=P)    # (B*L, E)
+        pool = run_mlp_concat(self.pts_encoder_2, g, taps[5], P, mode, glob_first=True, pool=P)
         taps2 = {5: None}
         pool = run_mlp(self.pts_mlp, pool, mode, taps=taps2)                             # (B*L, E); tap = after pts_mlp[5]
         gg = ops.group_max(pool, B, L)                                                   # (B, E)
-        cat = torch.cat([gg.view(B, 1, -1).expand(B, L, gg.shape[1]), taps2[5].view(B, L, -1)], dim=2)
-        out = run_mlp(self.regression_mlp, cat.reshape(B * L, -1).contiguous(), mode)
+        out = run_mlp_concat(self.regression_mlp, gg, taps2[5], L, mode, glob_first=True)
         preds = {t: torch.sigmoid(run_mlp(self.heads[t], out, mode).view(B, L, 1)) for t in ('score_reg', 'iou_reg')}
         self.preds_dict.update(preds)
         data_dict['pred_score'] = torch.sqrt(preds['score_reg'].squeeze(2) * preds['iou_reg'].squeeze(2))

@@ -247,6 +247,16 @@ int dz_points_in_boxes_mask(const float* points, int n_pts, int pt_stride, const
  * Replaces F.linear and the Conv1d/Conv2d(k=1)+BN+ReLU MLP stacks (utils/detzero_utils/model_utils.py:81-134). */
 int dz_linear_fwd(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift,
                   int relu, float* y, int ldy, int mode, dz_stream_t stream);
+/* The same with a per-row-GROUP shift: y[m] = act((x[m] W^T) * scale + shift + gshift[m / gsize]), gshift (M/gsize, N).  Serves the
+ * PointNet "concatenate the max-pooled global feature back onto every point, then Linear" step (position_transformer.py:118-123,
+ * geometry_transformer.py:131-136, confidence_pointnet.py:88-100) without materialising the concatenation: W = [W_g | W_p],
+ * gshift = (g W_g^T) * scale computed once per group, x = the per-point half. */
+int dz_linear_fwd_grouped(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift,
+                          const float* gshift, int gsize, int relu, float* y, int ldy, int mode, dz_stream_t stream);
+/* Linear (+folded BN +ReLU) fused with the max over groups of `group` consecutive rows (group % 128 == 0, K % 32 == 0, N % 4 == 0,
+ * tensor-core mode): y (M/group, N).  The last layer of a PointNet encoder + torch.max over the points in one kernel. */
+int dz_linear_max_fwd(const float* x, int M, int K, const float* w, int N, const float* scale, const float* shift, int relu,
+                      int group, float* y, int mode, dz_stream_t stream);
 /* max over `group` consecutive rows: x (G*group, C) -> y (G, C)  (torch.max over points,
  * position_transformer.py:109,118) */
 int dz_group_max(const float* x, int G, int group, int C, float* y, dz_stream_t stream);
