@@ -109,3 +109,31 @@ def test_crm_vs_reference_golden(cuda, mode, tol):
     m = m.to(cuda)
     d = m(_to(ri.crm_inputs(SEED + 2), cuda))
     assert (d['pred_score'].cpu() - torch.from_numpy(GOLD['crm.pred_score'])).abs().max().item() < tol
+
+
+def test_grouped_linear_and_fused_maxpool(cuda):
+    """dz_linear_fwd_grouped == Linear(cat([global.expand, per-row])) and dz_linear_max_fwd == max over groups of Linear(...):
+    the two PointNet fusions of the refiner, against plain PyTorch fp32"""
+    from detzero_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    G, gsize, Cg, Cp, N = 5, 384, 256, 128, 512
+    glob, per = torch.randn(G, Cg, generator=g), torch.randn(G * gsize, Cp, generator=g)
+    w = torch.randn(N, Cg + Cp, generator=g) * 0.05
+    sc, sh = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+    cat = torch.cat([glob[:, None, :].expand(G, gsize, Cg), per.view(G, gsize, Cp)], dim=2).reshape(G * gsize, -1)
+    ref = torch.relu((cat @ w.t()) * sc + sh)
+    for mode, tol in ((_lib.DZ_F32, 1e-5), (_lib.DZ_TF32, 3e-3)):
+        rnd = ops.round_tf32 if mode == _lib.DZ_TF32 else (lambda t: t)
+        gshift = ops.linear(glob.to(cuda), rnd(w[:, :Cg].contiguous()).to(cuda), sc.to(cuda), None, False, mode=mode)
+        out = ops.linear_grouped(per.to(cuda), rnd(w[:, Cg:].contiguous()).to(cuda), gshift, gsize, sc.to(cuda), sh.to(cuda), True, mode=mode)
+        assert util.rel_err(out.cpu(), ref) < tol, mode
+    # fused last layer + max over the points of a crop (group = 256 rows), incl. a group count that leaves a partial last CTA wave
+    for G2, group in ((37, 256), (3, 4096)):
+        x = torch.randn(G2 * group, 128, generator=g)
+        w2 = torch.randn(256, 128, generator=g) * 0.1
+        sc2, sh2 = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+        for relu in (True, False):
+            y = (x @ w2.t()) * sc2 + sh2
+            ref2 = (torch.relu(y) if relu else y).view(G2, group, 256).max(dim=1)[0]
+            out = ops.linear_max(x.to(cuda), ops.round_tf32(w2).to(cuda), group, sc2.to(cuda), sh2.to(cuda), relu, mode=_lib.DZ_TF32)
+            assert util.rel_err(out.cpu(), ref2) < 3e-3, (G2, group, relu)
