@@ -55,11 +55,63 @@ extern "C" int dz_debug_conv2d_trace(long long* host) {
     return cudaMemcpyFromSymbol(host, g_ct_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
 }
 
-template <int BN, int MT, int OCC>
-__global__ void __launch_bounds__(CT_THREADS, OCC)
-k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
-              Conv2dParams p, int tiles_x, int tiles_y) {
-    using Cfg = CtCfg<BN, MT, OCC>;
+// ---- CTA-pair variant (TWO = 1): a cluster of 2 CTAs (the two SMs of a TPC) owns two M tiles and ONE BN-wide weight tile.  Each CTA loads
+// its own activation patch and HALF of the weight rows (TMA .cta_group::2: the bytes of both CTAs complete on the leader's mbarrier);
+// the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256 = 128 rows per CTA, N = BN) and its commits are multicast to both
+// CTAs' barriers.  Per SM and MMA the shared-memory port then moves A 4 KB + B BN/2 x 32 B (written once, read once) instead of
+// A 4 KB + B BN x 32 B: with TF32 operands the single-CTA kernel spends 128 clk of port time per 64 clk of tensor-pipe time at BN = 128
+// (profiles/r02_ncu_full_conv2d_batch8.json: 50-57 % tensor pipe); the pair needs 96, and at BN = 256 (Cout = 256 layers) 128 per 128.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int NCOLS> __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst) {          // one full warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_dst)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void mma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma2_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(tc::smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// TMA loads of a CTA pair: the transaction bytes go to the mbarrier of the pair's LEADER (bit 24 of the shared::cluster address
+// selects the CTA inside the pair; same trick as CUTLASS' SM100_TMA_2SM_LOAD)
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int BN, int MT, int OCC, int TWO>
+struct CtKCfg {
+    static constexpr int B_ROWS = TWO ? BN / 2 : BN;                     // weight rows this CTA holds
+    static constexpr int B_BYTES = B_ROWS * CT_BK * 4;
+    static constexpr int STAGE_BYTES = MT * CT_A_BYTES + B_BYTES;
+    static constexpr int BUDGET = OCC == 1 ? 200 * 1024 : 104 * 1024;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = (MT * BN) < 32 ? 32 : MT * BN;
+};
+
+template <int BN, int MT, int OCC, int TWO>
+__device__ __forceinline__ void conv2d_tf32_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                                                 const Conv2dParams& p, int tiles_x, int tiles_y, int tiles_total) {
+    using Cfg = CtKCfg<BN, MT, OCC, TWO>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -70,7 +122,8 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr = (p.dbg & 4) && blockIdx.x == 0 && blockIdx.y == 0;
     if (tr && threadIdx.x == 0) g_ct_trace[0] = clock64();
-    int mt = blockIdx.x;
+    int mt = min((int)blockIdx.x, tiles_total - 1);         // pair kernel: an odd tile count is padded with a duplicate of the last tile
+    const uint32_t rank = TWO ? cluster_ctarank() : 0u;     // (it recomputes and re-stores identical values)
     const int tx0 = (mt % tiles_x) * CT_TW; mt /= tiles_x;
     const int ty0 = (mt % tiles_y) * (CT_TH * MT);
     const int b = mt / tiles_y;
@@ -86,10 +139,12 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (TWO) { __syncthreads(); cluster_sync_all(); }       // both CTAs' barriers exist before anything cluster-scoped touches them
+    if (warp == 1) { if (TWO) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot); else tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
+    if (TWO) cluster_sync_all();
     const uint32_t tmem_base = *tmem_slot;
     if (tr && threadIdx.x == 0) g_ct_trace[1] = clock64();
 
@@ -103,6 +158,16 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 const int tap = it / cchunks, cc = it - tap * cchunks;
                 const int r = tap / p.KW, sx = tap - r * p.KW;
                 const bool ldA = !(p.dbg & 2) || it < Cfg::STAGES, ldB = !(p.dbg & 1) || it < Cfg::STAGES;
+                if (TWO) {
+                    // the leader's barrier collects the bytes of BOTH CTAs (each: its patch + its half of the weight rows)
+                    if (rank == 0) tc::mbar_arrive_expect_tx(full + s, 2 * (MT * CT_A_BYTES + Cfg::B_BYTES));
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tma2_load_4d(sa + m * CT_A_BYTES, &tmA, full + s, cc * CT_BK, tx0 * p.stride + sx - p.pad,
+                                     (ty0 + m * CT_TH) * p.stride + r - p.pad, b);
+                    tma2_load_2d(sb, &tmB, full + s, tap * p.cin + cc * CT_BK, n0 + (int)rank * Cfg::B_ROWS);
+                    continue;
+                }
                 tc::mbar_arrive_expect_tx(full + s, (ldA ? MT * CT_A_BYTES : 0) + (ldB ? Cfg::B_BYTES : 0));
                 if (ldA) {
 #pragma unroll
@@ -114,7 +179,27 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && TWO) {
+            if (rank == 0) {                                // the pair's leader issues every MMA; its commits reach both CTAs
+                constexpr uint32_t idesc2 = tc::instr_desc(2, 256, BN);
+                for (int it = 0; it < iters; ++it) {
+                    const int s = it % Cfg::STAGES;
+                    tc::mbar_wait(full + s, (it / Cfg::STAGES) & 1);
+                    tc::tcgen05_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint64_t bdesc = tc::smem_desc_sw128(sa + MT * CT_A_BYTES);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const uint64_t adesc = tc::smem_desc_sw128(sa + m * CT_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < CT_BK / 8; ++k)
+                            mma2_tf32(tmem_base + (uint32_t)(m * BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc2, (it | k) ? 1u : 0u);
+                    }
+                    mma2_commit_multicast(empty + s, 0b11);
+                }
+                mma2_commit_multicast(tmem_full, 0b11);
+            }
+        } else if (lane == 0) {
             constexpr uint32_t idesc = tc::instr_desc(2, 128, BN < 16 ? 16 : BN);
             for (int it = 0; it < iters; ++it) {
                 const int s = it % Cfg::STAGES;
@@ -189,7 +274,12 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 // epilogue as long as the main loop.  Here the warp's 32 pixels x 32 channels go to the (now idle) pipeline
                 // buffers in the 128B-swizzled box layout and ONE TMA store per warp writes them (edge tiles clipped by the
                 // tensor map, channel range clipped at out_coff + cout).
-                unsigned char* stg = smem + (mc / 32) * CT_A_BYTES + q * 4096;        // 32 rows x 128 B
+                // staging slots (16 KB each, 4 KB per warp) are carved from the pipeline buffers; each warp group owns half of them and a
+                // warp re-uses its 4 KB only after its own earlier TMA store has read it (BN = 256 pair kernel: 4 chunks, 3 slots per group)
+                constexpr int SLOTS_H = (Cfg::STAGES * Cfg::STAGE_BYTES / CT_A_BYTES) / 2;
+                const int cj = (mc - half * PER) / 32;
+                if (cj >= SLOTS_H) { if (lane == 0) tc::tma_store_wait_read(); __syncwarp(); }
+                unsigned char* stg = smem + (half * SLOTS_H + cj % SLOTS_H) * CT_A_BYTES + q * 4096;        // 32 rows x 128 B
                 const uint32_t stg_u = tc::smem_u32(stg) + (uint32_t)((lane >> 3) * 1024 + (lane & 7) * 128);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -240,12 +330,44 @@ k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tc::tcgen05_fence_before();
     __syncthreads();
     if (tr && threadIdx.x == 0) g_ct_trace[4] = clock64();
-    if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (TWO) cluster_sync_all();                            // the peer's shared memory / TMEM stay alive until the pair is done
+    if (warp == 1) { if (TWO) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base); else tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+template <int BN, int MT, int OCC>
+__global__ void __launch_bounds__(CT_THREADS, OCC)
+k_conv2d_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+              Conv2dParams p, int tiles_x, int tiles_y) {
+    conv2d_tf32_body<BN, MT, OCC, 0>(tmA, tmB, tmO, p, tiles_x, tiles_y, 0x7fffffff);
+}
+
+template <int BN, int OCC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CT_THREADS, OCC)
+k_conv2d_tf32_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                   Conv2dParams p, int tiles_x, int tiles_y, int tiles_total) {
+    conv2d_tf32_body<BN, 1, OCC, 1>(tmA, tmB, tmO, p, tiles_x, tiles_y, tiles_total);
+}
+
+template <int BN, int OCC>
+static int launch_tf32_pair(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t st) {
+    using Cfg = CtKCfg<BN, 1, OCC, 1>;
+    static bool configured = false;
+    if (!configured) {
+        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32_pair<BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        configured = true;
+    }
+    const int tiles_x = dz_cdiv(p.Wo, CT_TW), tiles_y = dz_cdiv(p.Ho, CT_TH);
+    const int tiles = tiles_x * tiles_y * p.B;
+    dim3 grid((tiles + 1) / 2 * 2, dz_cdiv(p.cout, BN));
+    static_assert(Cfg::STAGES * Cfg::STAGE_BYTES / CT_A_BYTES >= 2, "epilogue staging needs at least one slot per warp group");
+    k_conv2d_tf32_pair<BN, OCC><<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmO, p, tiles_x, tiles_y, tiles);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
 }
 
 template <int BN, int MT, int OCC = 1>
 static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t st) {
-    using Cfg = CtCfg<BN, MT, OCC>;
+    using Cfg = CtKCfg<BN, MT, OCC, 0>;
     static bool configured = false;
     if (!configured) {
         DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32<BN, MT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -282,11 +404,20 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
     int bn = p.cout > 128 ? 128 : (p.cout > 64 ? 128 : (p.cout > 32 ? 64 : 32));
+    // CTA-pair kernel (tcgen05 cta_group::2): real convolutions with Cout a multiple of 128 and at least one tile pair per SM pair
+    static const int use_pair = getenv("DZ_CONV2D_2SM") ? atoi(getenv("DZ_CONV2D_2SM")) : 1;
+    const long long tiles_m = (long long)dz_cdiv(p.Wo, CT_TW) * dz_cdiv(p.Ho, CT_TH) * p.B;
+    // Measured (profiles/r02_spconv_notes.md): the pair pays off where it makes a 256-wide tile possible (256 -> 256 @94^2: 158 -> 120 us,
+    // 1x1 128 -> 256: 110 -> 80 us); with BN = 128 it is no faster than two co-resident single CTAs (128 -> 128 @188^2: 177 vs 182 us),
+    // so Cout % 256 != 0 keeps the single-CTA kernel.  DZ_CONV2D_2SM=0 switches the pair kernel off, =128 forces it for Cout % 128 == 0.
+    const bool pair = use_pair && !p.gmax && !p.gshift && tiles_m * (p.cout / 128) >= 2 * DZ_NUM_SMS &&
+                      (use_pair == 128 ? p.cout % 128 == 0 : p.cout % 256 == 0);
+    const int bn_pair = (p.cout % 256 == 0 && use_pair != 128) ? 256 : 128;
     {
         cuuint64_t ktot = (cuuint64_t)p.KH * p.KW * p.cin;
         cuuint64_t dims[2] = {ktot, (cuuint64_t)p.cout};
         cuuint64_t strides[1] = {ktot * 4};
-        cuuint32_t box[2] = {(cuuint32_t)CT_BK, (cuuint32_t)bn};
+        cuuint32_t box[2] = {(cuuint32_t)CT_BK, (cuuint32_t)(pair ? bn_pair / 2 : bn)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -306,6 +437,7 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
+    if (pair) return bn_pair == 256 ? launch_tf32_pair<256, 2>(p, tmA, tmB, tmO, st) : launch_tf32_pair<128, 2>(p, tmA, tmB, tmO, st);
     // two stacked patches per CTA when there are enough tiles to still fill the GPU (the weight tile is then loaded once
     // for 256 output pixels)
     const long long tiles1 = (long long)dz_cdiv(p.Wo, CT_TW) * dz_cdiv(p.Ho, CT_TH) * p.B * dz_cdiv(p.cout, bn);

@@ -649,3 +649,24 @@ def test_frame_major_schedule(cuda):
         b = ops.spconv_fwd(fin, tab, d_n, cap, wp, None, None, None, True, mode, kshape=(27, cin, cout), row_order=order, layout='row',
                            tab_tiles=tab_tiles if P else None)
         assert torch.equal(a[:n], b[:n]), mode
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,pad,H,W,B,coff,cstride', [(128, 128, 3, 1, 1, 188, 188, 2, 0, 128), (256, 256, 3, 1, 1, 94, 94, 8, 0, 256),
+                                                                      (128, 256, 3, 2, 1, 187, 189, 4, 0, 256), (256, 128, 3, 1, 1, 100, 84, 4, 64, 256),
+                                                                      (128, 256, 1, 1, 0, 150, 150, 2, 256, 512)])
+def test_conv2d_tf32_cta_pair_kernel(cuda, cin, cout, k, stride, pad, H, W, B, coff, cstride):
+    """enough tiles for the CTA-pair kernel (tcgen05 cta_group::2: two M tiles share one weight tile, each CTA loads half of its rows;
+    BN = 256 for Cout = 256): odd tile counts (duplicate tail tile), ragged edges, stride 2, channel-offset (concat) output"""
+    from detzero_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * 0.05
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x, w, None, stride, pad) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    out = torch.full((B, Ho, Wo, cstride), -3.0, device=cuda)
+    ops.conv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), ops.pack_conv_weight(w, _lib.DZ_TF32).to(cuda), (k, k, cin, cout), stride, pad,
+               scale.to(cuda), shift.to(cuda), True, out=out, out_coff=coff, mode=_lib.DZ_TF32)
+    got = out[..., coff:coff + cout].permute(0, 3, 1, 2).cpu()
+    assert util.rel_err(got, ref) < 2e-3
+    assert torch.all(out[..., :coff] == -3.0) and torch.all(out[..., coff + cout:] == -3.0)
