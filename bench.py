@@ -429,9 +429,24 @@ def sparse_conv_roofline(det, layer_times, batch, storage_bytes=4):
     achieved = tot_bytes / (tot_ms / 1000.0) / 1e9 if tot_ms > 0 else 0.0
     return {'bound': 'hbm', 'kernel': 'sparse conv (all %d sparse-conv launches of one step)' % len(rec), 'achieved': achieved,
             'peak': peak, 'peak_source': which, 'unit': 'GB/s', 'frac': achieved / peak,
-            'traffic': None, 'traffic_note': 'not measured in this run; the ncu --set full capture of the same launches is committed under profiles/',
+            'traffic': committed_traffic(det, batch), 'traffic_source': 'committed ncu --set full capture of the same 14 launches '
+            '(profiles/r02_ncu_full_spconv_bf16x2_batch8.json, dram__bytes_read.sum + dram__bytes_write.sum); NOT measured in this run -- null for '
+            'any other mode / batch / backbone',
             'algorithmic_bytes_per_step': tot_bytes, 'storage_bytes_per_value': s, 'algorithmic_flops_per_step': tot_flops,
             'ms_per_step': tot_ms, 'frames_per_step': batch, 'layers': layers}
+
+
+def committed_traffic(det, batch):
+    """DRAM bytes per step of the sparse-conv launches from the committed ncu capture -- only for the exact configuration it was taken on"""
+    path = os.path.join(ROOT, 'profiles', 'r02_ncu_full_spconv_bf16x2_batch8.json')
+    try:
+        mode = det.model.backbone3d.model_cfg.get('COMPUTE_MODE')
+        if mode == 'bf16x2' and batch == 8 and type(det.model.backbone3d).__name__ == 'VoxelBackBone8x' and os.path.exists(path):
+            j = json.load(open(path))
+            return (j['dram_read_MB'] + j['dram_write_MB']) * 1e6
+    except Exception:
+        pass
+    return None
 
 
 SP_DTYPE = {'fp32': 'fp32 FMA', 'tf32x3': 'tf32x3 (3 TF32 passes, fp32-level)',
