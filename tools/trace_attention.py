@@ -24,6 +24,11 @@ buf = np.zeros(64, np.int64)
 l.dz_debug_attention_trace(buf.ctypes.data, 0)
 n = buf[24]
 print('blocks', n)
+if not os.environ.get('DZ_ATTN_TWO_PASS'):
+    print('loader : wait k_empty %d, wait v_empty %d, V^T work %d, total %d' % tuple(buf[0:4]))
+    print('mma    : wait k_full %d, wait s_empty %d, wait v_full %d, wait p_full %d, wait o_empty %d | total %d' % (tuple(buf[8:13]) + (buf[14],)))
+    print('softmax: wait s_full %d, ld S + max %d, bar.sync %d, exp %d, wait p_empty %d, write P %d, wait o_full %d, fold %d | total %d' % (tuple(buf[16:24]) + (buf[25],)))
+    sys.exit(0)
 print('loader : wait k_empty %d, wait v_empty %d, V^T work %d, total %d' % tuple(buf[0:4]))
 print('mma    : wait k_full %d, wait s_empty %d, wait v_full %d, wait p_full %d, issue S %d, issue PV %d | pass1 end %d, total %d' % (tuple(buf[8:14]) + (buf[15], buf[14])))
 print('softmax: p1 wait s_full %d, p1 body %d | p2 wait s_full %d, wait p_empty %d, body %d | pass1 end %d total %d' % (tuple(buf[16:21]) + (buf[23], buf[22])))
