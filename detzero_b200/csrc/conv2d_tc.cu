@@ -382,6 +382,265 @@ static int launch_tf32(const Conv2dParams& p, const CUtensorMap& tmA, const CUte
     return DZ_OK;
 }
 
+// =====================================================================================================================
+// HALO kernel: 3x3 stride-1 convolutions (16 of the 22 dense convs of the BEV backbone + head).
+//
+// The generic kernel above re-reads its 128-pixel activation patch from L2 once per filter tap: 9 x 16 KB per 32-channel slice, and with
+// three 32 KB stages per CTA the SM cannot keep enough bytes in flight to cover the L2 latency at the tensor pipe's rate (50-57 % tensor
+// pipe in profiles/r02_ncu_full_conv2d_batch8.json, nothing else saturated).  Here the CTA loads the (16+2) x (8+2) pixel HALO of its
+// 16 x 8 output patch ONCE per 32-channel slice (23 KB) and the nine taps are nine A descriptors into that one tile: the UMMA
+// shared-memory descriptor may start at any 128-byte pixel row, its 8-row core groups are the 8-pixel rows of the patch, and the stride
+// between groups (SBO) is the halo's row pitch, 10 pixels = 1280 B -- the 128-byte swizzle is a function of the absolute shared-memory
+// address, so a window shifted by (r, s) reads exactly the bytes the TMA unit wrote for pixel (y + r, x + s) (tools/ubench_halo.cu checks
+// all nine taps).  Per slice the SM now pulls 23 KB + 9 weight tiles instead of 9 x (16 KB + weight tile).
+// TWO = 1: CTA pair as above (each CTA its own halo, half of the weight rows, tcgen05.mma.cta_group::2).
+// =====================================================================================================================
+static constexpr int HL_TH = 16, HL_TW = 8, HL_PITCH = HL_TW + 2, HL_ROWS = HL_TH + 2;
+static constexpr int HL_A_BYTES = HL_ROWS * HL_PITCH * 128;          // 23040 B delivered by the TMA unit
+static constexpr int HL_A_SLOT = (HL_A_BYTES + 1023) / 1024 * 1024;  // 23552: slots stay 1024-byte aligned (swizzle phase)
+static constexpr int HL_A_STAGES = 2;
+
+template <int BN, int TWO>
+struct HlCfg {
+    static constexpr int B_ROWS = TWO ? BN / 2 : BN;
+    static constexpr int B_BYTES = B_ROWS * 128;
+    static constexpr int BUDGET = 104 * 1024;                         // two CTAs per SM
+    static constexpr int B_STAGES = (BUDGET - HL_A_STAGES * HL_A_SLOT) / B_BYTES > 9 ? 9 : (BUDGET - HL_A_STAGES * HL_A_SLOT) / B_BYTES;
+    static constexpr int BUF = HL_A_STAGES * HL_A_SLOT + B_STAGES * B_BYTES;
+    static constexpr int SMEM = BUF + 1024 + 256;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int TWO>
+__device__ __forceinline__ void conv2d_halo_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const Conv2dParams& p,
+                                                 int tiles_x, int tiles_y, int tiles_total) {
+    using Cfg = HlCfg<BN, TWO>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smB = smem + HL_A_STAGES * HL_A_SLOT;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::BUF);
+    uint64_t* a_empty = a_full + HL_A_STAGES;
+    uint64_t* b_full = a_empty + HL_A_STAGES;
+    uint64_t* b_empty = b_full + Cfg::B_STAGES;
+    uint64_t* tmem_full = b_empty + Cfg::B_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int mt = min((int)blockIdx.x, tiles_total - 1);         // pair kernel: an odd tile count is padded with a duplicate of the last tile
+    const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+    const int tx0 = (mt % tiles_x) * HL_TW; mt /= tiles_x;
+    const int ty0 = (mt % tiles_y) * HL_TH;
+    const int b = mt / tiles_y;
+    const int n0 = blockIdx.y * BN;
+    const int cchunks = p.cin / CT_BK;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        tc::prefetch_tmap(&tmO);
+        for (int s = 0; s < HL_A_STAGES; ++s) { tc::mbar_init(a_full + s, 1); tc::mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < Cfg::B_STAGES; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (TWO) { __syncthreads(); cluster_sync_all(); }
+    if (warp == 1) { if (TWO) tmem_alloc2<Cfg::TMEM_COLS>(tmem_slot); else tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    if (TWO) cluster_sync_all();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int bit = 0;
+            for (int cc = 0; cc < cchunks; ++cc) {
+                const int a = cc % HL_A_STAGES;
+                tc::mbar_wait(a_empty + a, ((cc / HL_A_STAGES) & 1) ^ 1);
+                if (TWO) {
+                    if (rank == 0) tc::mbar_arrive_expect_tx(a_full + a, 2 * HL_A_BYTES);
+                    tma2_load_4d(smem + a * HL_A_SLOT, &tmA, a_full + a, cc * CT_BK, tx0 - p.pad, ty0 - p.pad, b);
+                } else {
+                    tc::mbar_arrive_expect_tx(a_full + a, HL_A_BYTES);
+                    tc::tma_load_4d(smem + a * HL_A_SLOT, &tmA, a_full + a, cc * CT_BK, tx0 - p.pad, ty0 - p.pad, b);
+                }
+                for (int tap = 0; tap < 9; ++tap, ++bit) {
+                    const int s = bit % Cfg::B_STAGES;
+                    tc::mbar_wait(b_empty + s, ((bit / Cfg::B_STAGES) & 1) ^ 1);
+                    if (TWO) {
+                        if (rank == 0) tc::mbar_arrive_expect_tx(b_full + s, 2 * Cfg::B_BYTES);
+                        tma2_load_2d(smB + s * Cfg::B_BYTES, &tmB, b_full + s, tap * p.cin + cc * CT_BK, n0 + (int)rank * Cfg::B_ROWS);
+                    } else {
+                        tc::mbar_arrive_expect_tx(b_full + s, Cfg::B_BYTES);
+                        tc::tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, b_full + s, tap * p.cin + cc * CT_BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && (!TWO || rank == 0)) {                 // pair: the leader issues every MMA; its commits reach both CTAs
+            constexpr uint32_t idesc = tc::instr_desc(2, TWO ? 256 : 128, BN);
+            int bit = 0;
+            for (int cc = 0; cc < cchunks; ++cc) {
+                const int a = cc % HL_A_STAGES;
+                tc::mbar_wait(a_full + a, (cc / HL_A_STAGES) & 1);
+                const uint32_t ha = tc::smem_u32(smem + a * HL_A_SLOT);
+                for (int tap = 0; tap < 9; ++tap, ++bit) {
+                    const int s = bit % Cfg::B_STAGES;
+                    tc::mbar_wait(b_full + s, (bit / Cfg::B_STAGES) & 1);
+                    tc::tcgen05_fence_after();
+                    const int r = tap / 3, sx = tap - r * 3;
+                    // window (r, sx) of the halo: start at pixel (r, sx), 8-pixel rows HL_PITCH pixels apart
+                    const uint32_t a0 = ha + (uint32_t)((r * HL_PITCH + sx) * 128);
+                    const uint64_t adesc = (uint64_t)((a0 >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((HL_PITCH * 128) >> 4) << 32) |
+                                           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                    const uint64_t bdesc = tc::smem_desc_sw128(tc::smem_u32(smB + s * Cfg::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < CT_BK / 8; ++k) {
+                        if (TWO) mma2_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (bit | k) ? 1u : 0u);
+                        else tc::mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (bit | k) ? 1u : 0u);
+                    }
+                    if (TWO) mma2_commit_multicast(b_empty + s, 0b11); else tc::mma_commit(b_empty + s);
+                }
+                if (TWO) mma2_commit_multicast(a_empty + a, 0b11); else tc::mma_commit(a_empty + a);
+            }
+            if (TWO) mma2_commit_multicast(tmem_full, 0b11); else tc::mma_commit(tmem_full);
+        }
+    } else {
+        // epilogue: folded BN / bias / ReLU, staged through the (idle) pipeline buffers, one TMA store of 4 patch rows x 8 pixels x 32
+        // channels per warp and 32-column chunk
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        tc::mbar_wait(tmem_full, 0);
+        tc::tcgen05_fence_after();
+        constexpr int PER = BN >= 64 ? BN / 2 : BN;             // BN = 32: one 32-column chunk, the second warp group has nothing to do
+        constexpr int SLOTS_H = (Cfg::BUF / CT_A_BYTES) / 2;
+        static_assert(SLOTS_H >= 1, "epilogue staging needs one 16 KB slot per warp group");
+        if (half == 1 && BN < 64) { /* nothing */ } else
+#pragma unroll 1
+        for (int mc = half * PER; mc < half * PER + PER; mc += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mc, v);
+            const int cj = (mc - half * PER) / 32;
+            if (cj >= SLOTS_H) { if (lane == 0) tc::tma_store_wait_read(); __syncwarp(); }
+            unsigned char* stg = smem + (half * SLOTS_H + cj % SLOTS_H) * CT_A_BYTES + q * 4096;        // 32 rows x 128 B
+            const uint32_t stg_u = tc::smem_u32(stg) + (uint32_t)((lane >> 3) * 1024 + (lane & 7) * 128);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int n = n0 + mc + j;
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (n < p.cout) {
+                    if (p.scale) { float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n)); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+                    if (p.shift) { float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n)); o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w; }
+                }
+                if (p.relu) {
+                    o.x = tc::rna_tf32(fmaxf(o.x, 0.f)); o.y = tc::rna_tf32(fmaxf(o.y, 0.f));
+                    o.z = tc::rna_tf32(fmaxf(o.z, 0.f)); o.w = tc::rna_tf32(fmaxf(o.w, 0.f));
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4)),
+                             "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && n0 + mc < p.cout) {
+                tc::tma_store_4d(&tmO, stg, p.out_coff + n0 + mc, tx0, ty0 + q * 4, b);      // rows q*4 .. q*4+3 of the 16 x 8 patch
+                tc::tma_store_commit();
+            }
+        }
+    }
+    if (warp >= 2 && lane == 0) tc::tma_store_wait_read();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (TWO) cluster_sync_all();
+    if (warp == 1) { if (TWO) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base); else tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+k_conv2d_tf32_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                   Conv2dParams p, int tiles_x, int tiles_y) {
+    conv2d_halo_body<BN, 0>(tmA, tmB, tmO, p, tiles_x, tiles_y, 0x7fffffff);
+}
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CT_THREADS, 2)
+k_conv2d_tf32_halo_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                        Conv2dParams p, int tiles_x, int tiles_y, int tiles_total) {
+    conv2d_halo_body<BN, 1>(tmA, tmB, tmO, p, tiles_x, tiles_y, tiles_total);
+}
+
+template <int BN>
+static int launch_halo_single(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, int tiles_x, int tiles_y,
+                              cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32_halo<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HlCfg<BN, 0>::SMEM));
+        configured = true;
+    }
+    dim3 grid(tiles_x * tiles_y * p.B, dz_cdiv(p.cout, BN));
+    k_conv2d_tf32_halo<BN><<<grid, CT_THREADS, HlCfg<BN, 0>::SMEM, st>>>(tmA, tmB, tmO, p, tiles_x, tiles_y);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
+}
+template <int BN>
+static int launch_halo_pair(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, int tiles_x, int tiles_y,
+                            cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32_halo_pair<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HlCfg<BN, 1>::SMEM));
+        configured = true;
+    }
+    const int tiles = tiles_x * tiles_y * p.B;
+    dim3 grid((tiles + 1) / 2 * 2, dz_cdiv(p.cout, BN));
+    k_conv2d_tf32_halo_pair<BN><<<grid, CT_THREADS, HlCfg<BN, 1>::SMEM, st>>>(tmA, tmB, tmO, p, tiles_x, tiles_y, tiles);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
+}
+
+// mode (DZ_CONV2D_HALO): 1 = automatic -- CTA pair with a 256-wide weight tile when Cout % 256 == 0 (256 -> 256 @94^2, 8 frames: 114 -> 103 us),
+// otherwise one CTA per patch (128 -> 128 @188^2: 177 -> 138 us; the BN = 128 pair is slower, 152 us); 2 = pair whenever Cout % 128 == 0;
+// 3 = never pair
+static int launch_halo(const Conv2dParams& p, int mode, cudaStream_t st) {
+    tc::EncodeTiledFn enc = tc::get_encode_tiled();
+    CUtensorMap tmA, tmB, tmO;
+    const bool pair = mode != 3 && ((p.cout % 256 == 0) || (mode == 2 && p.cout % 128 == 0));
+    const int bn = pair ? (p.cout % 256 == 0 ? 256 : 128) : (p.cout > 64 ? 128 : (p.cout > 32 ? 64 : 32));
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)p.in_cstride, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.in_cstride * 4, (cuuint64_t)p.W * p.in_cstride * 4, (cuuint64_t)p.H * p.W * p.in_cstride * 4};
+        cuuint32_t box[4] = {(cuuint32_t)CT_BK, (cuuint32_t)HL_PITCH, (cuuint32_t)HL_ROWS, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(halo A) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
+    {
+        cuuint64_t ktot = (cuuint64_t)9 * p.cin;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)p.cout};
+        cuuint64_t strides[1] = {ktot * 4};
+        cuuint32_t box[2] = {(cuuint32_t)CT_BK, (cuuint32_t)(pair ? bn / 2 : bn)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(halo B) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)(p.out_coff + p.cout), (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.out_cstride * 4, (cuuint64_t)p.OW * p.out_cstride * 4, (cuuint64_t)p.OH * p.OW * p.out_cstride * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)HL_TW, 4, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(halo out) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    }
+    const int tiles_x = dz_cdiv(p.Wo, HL_TW), tiles_y = dz_cdiv(p.Ho, HL_TH);
+    if (pair) return bn == 256 ? launch_halo_pair<256>(p, tmA, tmB, tmO, tiles_x, tiles_y, st) : launch_halo_pair<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+    switch (bn) {
+        case 128: return launch_halo_single<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+        case 64: return launch_halo_single<64>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+        default: return launch_halo_single<32>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+    }
+}
+
 // p.w must be in (cout, KH, KW, cin) layout for this path
 int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
     Conv2dParams p = p_in;
@@ -437,6 +696,11 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
+    // 3x3 stride-1 convolutions: the halo kernel (DZ_CONV2D_HALO: 0 = off, 1 = single CTA, 2 = CTA pair)
+    static const int halo = getenv("DZ_CONV2D_HALO") ? atoi(getenv("DZ_CONV2D_HALO")) : 1;
+    if (halo && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.tma_store && !p.gshift && !(p.dbg & 3) &&
+        tiles_m * dz_cdiv(p.cout, 128) >= 2 * DZ_NUM_SMS)
+        return launch_halo(p, halo, st);
     if (pair) return bn_pair == 256 ? launch_tf32_pair<256, 2>(p, tmA, tmB, tmO, st) : launch_tf32_pair<128, 2>(p, tmA, tmB, tmO, st);
     // two stacked patches per CTA when there are enough tiles to still fill the GPU (the weight tile is then loaded once
     // for 256 output pixels)

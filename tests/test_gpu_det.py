@@ -653,10 +653,15 @@ def test_frame_major_schedule(cuda):
 
 @pytest.mark.parametrize('cin,cout,k,stride,pad,H,W,B,coff,cstride', [(128, 128, 3, 1, 1, 188, 188, 2, 0, 128), (256, 256, 3, 1, 1, 94, 94, 8, 0, 256),
                                                                       (128, 256, 3, 2, 1, 187, 189, 4, 0, 256), (256, 128, 3, 1, 1, 100, 84, 4, 64, 256),
-                                                                      (128, 256, 1, 1, 0, 150, 150, 2, 256, 512)])
+                                                                      (128, 256, 1, 1, 0, 150, 150, 2, 256, 512),
+                                                                      # 3x3 stride-1 -> the halo kernel at every tile width: 64 (shared conv), 32 with a
+                                                                      # ragged Cout (fused head stage 2), 3 x 128 (fused head stage 1), ragged image edges
+                                                                      (512, 64, 3, 1, 1, 188, 188, 2, 0, 64), (384, 12, 3, 1, 1, 100, 90, 4, 0, 12),
+                                                                      (64, 384, 3, 1, 1, 95, 93, 4, 0, 384), (128, 128, 3, 1, 1, 61, 67, 8, 128, 384)])
 def test_conv2d_tf32_cta_pair_kernel(cuda, cin, cout, k, stride, pad, H, W, B, coff, cstride):
     """enough tiles for the CTA-pair kernel (tcgen05 cta_group::2: two M tiles share one weight tile, each CTA loads half of its rows;
-    BN = 256 for Cout = 256): odd tile counts (duplicate tail tile), ragged edges, stride 2, channel-offset (concat) output"""
+    BN = 256 for Cout = 256) and, for 3x3 stride-1 shapes, the HALO kernel (one (16+2) x (8+2) activation tile per 32-channel slice, nine
+    shifted UMMA descriptors): odd tile counts (duplicate tail tile), ragged edges, stride 2, channel-offset (concat) output"""
     from detzero_b200 import ops
     g = torch.Generator().manual_seed(13)
     x = torch.randn(B, cin, H, W, generator=g)

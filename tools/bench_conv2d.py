@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from detzero_b200 import ops, _lib
 cin, cout, hw = [int(v) for v in (sys.argv[1:4] + [128, 128, 188][len(sys.argv) - 1:])][:3]
 dev = torch.device('cuda')
-x = torch.randn(1, hw, hw, cin, device=dev)
+NB = int(os.environ.get('BATCH', 1))
+x = torch.randn(NB, hw, hw, cin, device=dev)
 w = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3) * 0.05, _lib.DZ_TF32).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ts = []
@@ -21,8 +22,8 @@ for i in range(13):
     torch.cuda.synchronize()
     if i >= 3: ts.append(e0.elapsed_time(e1) * 1000)
 ts.sort()
-fl = 2.0 * hw * hw * cin * cout * 9
-print('DZ_CONV2D_DBG=%s conv %d->%d 3x3 @%d^2: median %.1f us  (%.0f TFLOP/s)' % (os.environ.get('DZ_CONV2D_DBG', '0'), cin, cout, hw, ts[len(ts) // 2], fl / ts[len(ts) // 2] / 1e6))
+fl = 2.0 * NB * hw * hw * cin * cout * 9
+print('DZ_CONV2D_DBG=%s HALO=%s batch %d conv %d->%d 3x3 @%d^2: median %.1f us  (%.0f TFLOP/s)' % (os.environ.get('DZ_CONV2D_DBG', '0'), os.environ.get('DZ_CONV2D_HALO', '-'), NB, cin, cout, hw, ts[len(ts) // 2], fl / ts[len(ts) // 2] / 1e6))
 # steady state: a CUDA graph of 10 back-to-back convs (x -> y -> x ...): no host latency, warm L2, real launch gaps
 if cin == cout:
     y = torch.empty_like(x)
