@@ -303,7 +303,15 @@ __device__ __forceinline__ void conv2d_tf32_body(const CUtensorMap& tmA, const C
                 tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA (async proxy)
                 __syncwarp();
                 if (lane == 0 && n0 + c0 < p.cout) {
-                    tc::tma_store_4d(&tmO, stg, p.out_coff + n0 + c0, tx0, ty0 + m * CT_TH + q * 2, b);
+                    const int row0 = ty0 + m * CT_TH + q * 2;
+                    if (p.tma_store == 2) {
+                        // ConvTranspose2d with kernel == stride: output pixel (y*os + oy0, x*os + ox0) through the 5-D view
+                        // [C][dx][x][dy][b*Ho + y] of the NHWC tensor.  The merged (batch, y) axis cannot clip rows past Ho: skip them
+                        // (Ho is even and row0 is even, so a 2-row box is either entirely inside or entirely outside)
+                        if (row0 < p.Ho) tc::tma_store_5d(&tmO, stg, p.out_coff + n0 + c0, p.ox0, tx0, p.oy0, b * p.Ho + row0);
+                    } else {
+                        tc::tma_store_4d(&tmO, stg, p.out_coff + n0 + c0, tx0, row0, b);
+                    }
                     tc::tma_store_commit();
                 }
             } else if (valid) {
@@ -602,8 +610,8 @@ static int launch_halo_pair(const Conv2dParams& p, const CUtensorMap& tmA, const
 static int launch_halo(const Conv2dParams& p, int mode, cudaStream_t st) {
     tc::EncodeTiledFn enc = tc::get_encode_tiled();
     CUtensorMap tmA, tmB, tmO;
-    const bool pair = mode != 3 && ((p.cout % 256 == 0) || (mode == 2 && p.cout % 128 == 0));
-    const int bn = pair ? (p.cout % 256 == 0 ? 256 : 128) : (p.cout > 64 ? 128 : (p.cout > 32 ? 64 : 32));
+    const bool pair = mode != 3 && ((p.cout % 256 == 0) || (mode == 2 && (p.cout % 128 == 0 || p.cout == 64)));
+    const int bn = pair ? (p.cout % 256 == 0 ? 256 : (p.cout == 64 ? 64 : 128)) : (p.cout > 64 ? 128 : (p.cout > 32 ? 64 : 32));
     {
         cuuint64_t dims[4] = {(cuuint64_t)p.in_cstride, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
         cuuint64_t strides[3] = {(cuuint64_t)p.in_cstride * 4, (cuuint64_t)p.W * p.in_cstride * 4, (cuuint64_t)p.H * p.W * p.in_cstride * 4};
@@ -633,7 +641,8 @@ static int launch_halo(const Conv2dParams& p, int mode, cudaStream_t st) {
         if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(halo out) failed: %d", (int)r); return DZ_ERR_CUDA; }
     }
     const int tiles_x = dz_cdiv(p.Wo, HL_TW), tiles_y = dz_cdiv(p.Ho, HL_TH);
-    if (pair) return bn == 256 ? launch_halo_pair<256>(p, tmA, tmB, tmO, tiles_x, tiles_y, st) : launch_halo_pair<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+    if (pair) return bn == 256 ? launch_halo_pair<256>(p, tmA, tmB, tmO, tiles_x, tiles_y, st)
+                     : (bn == 64 ? launch_halo_pair<64>(p, tmA, tmB, tmO, tiles_x, tiles_y, st) : launch_halo_pair<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st));
     switch (bn) {
         case 128: return launch_halo_single<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
         case 64: return launch_halo_single<64>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
@@ -686,7 +695,20 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
     static const int no_tma_store = getenv("DZ_CONV2D_NO_TMA_STORE") ? 1 : 0;
     p.tma_store = (!p.gmax && !no_tma_store && p.os == 1 && p.oy0 == 0 && p.ox0 == 0 && p.OH == p.Ho && p.OW == p.Wo && bn >= 32 &&
                    (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
-    if (p.tma_store) {
+    if (!p.tma_store && !p.gmax && !no_tma_store && p.os >= 2 && p.OH == p.Ho * p.os && p.OW == p.Wo * p.os && p.Ho % 2 == 0 && bn >= 32 &&
+        p.oy0 < p.os && p.ox0 < p.os && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+        // strided output (ConvTranspose2d as os*os 1x1 convs): 5-D view [C][dx][x][dy][b*Ho + y], one TMA store per warp as above instead of
+        // per-thread strided stores (256 -> 256 @94^2, 8 frames: 70 us per (dy, dx) with 14 % tensor pipe before)
+        p.tma_store = 2;
+        cuuint64_t dims[5] = {(cuuint64_t)(p.out_coff + p.cout), (cuuint64_t)p.os, (cuuint64_t)p.Wo, (cuuint64_t)p.os, (cuuint64_t)p.Ho * p.B};
+        cuuint64_t strides[4] = {(cuuint64_t)p.out_cstride * 4, (cuuint64_t)p.os * p.out_cstride * 4, (cuuint64_t)p.OW * p.out_cstride * 4,
+                                 (cuuint64_t)p.os * p.OW * p.out_cstride * 4};
+        cuuint32_t box[5] = {32, 1, (cuuint32_t)CT_TW, 1, 2};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { dz_set_error("cuTensorMapEncodeTiled(strided out) failed: %d", (int)r); return DZ_ERR_CUDA; }
+    } else if (p.tma_store) {
         // channels [0, out_coff + cout) of the (possibly wider, concatenated) output tensor: stores past cout are clipped
         cuuint64_t dims[4] = {(cuuint64_t)(p.out_coff + p.cout), (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.B};
         cuuint64_t strides[3] = {(cuuint64_t)p.out_cstride * 4, (cuuint64_t)p.OW * p.out_cstride * 4, (cuuint64_t)p.OH * p.OW * p.out_cstride * 4};
@@ -698,7 +720,7 @@ int dz_conv2d_fwd_tc(const Conv2dParams& p_in, int mode, cudaStream_t st) {
     }
     // 3x3 stride-1 convolutions: the halo kernel (DZ_CONV2D_HALO: 0 = off, 1 = single CTA, 2 = CTA pair)
     static const int halo = getenv("DZ_CONV2D_HALO") ? atoi(getenv("DZ_CONV2D_HALO")) : 1;
-    if (halo && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.tma_store && !p.gshift && !(p.dbg & 3) &&
+    if (halo && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.tma_store == 1 && !p.gshift && !(p.dbg & 3) &&
         tiles_m * dz_cdiv(p.cout, 128) >= 2 * DZ_NUM_SMS)
         return launch_halo(p, halo, st);
     if (pair) return bn_pair == 256 ? launch_tf32_pair<256, 2>(p, tmA, tmB, tmO, st) : launch_tf32_pair<128, 2>(p, tmA, tmB, tmO, st);

@@ -334,6 +334,24 @@ def test_deconv2d_fp32_concat(cuda, s):
         assert out[..., :16].abs().max().item() == 0
 
 
+@pytest.mark.parametrize('B,cin,cout,H,W,coff,ctot', [(3, 256, 256, 94, 94, 256, 512), (3, 64, 64, 10, 21, 0, 64), (2, 128, 96, 30, 17, 32, 160)])
+def test_deconv2d_tf32_strided_tma_store(cuda, B, cin, cout, H, W, coff, ctot):
+    """ConvTranspose2d(kernel = stride = 2) on the tensor-core path with an even Ho: the epilogue stores through the 5-D
+    [C][dx][x][dy][b*Ho + y] view of the NHWC output (rows past Ho of the last tile are skipped, not wrapped into the next frame;
+    pixels past Wo are clipped), into a channel slice of a wider (concatenated) tensor"""
+    from detzero_b200 import ops
+    g = torch.Generator().manual_seed(B + H)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cin, cout, 2, 2, generator=g) * 0.05
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv_transpose2d(x, w, None, stride=2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    out = torch.full((B, 2 * H, 2 * W, ctot), -3.0, device=cuda)
+    ops.deconv2d(x.permute(0, 2, 3, 1).contiguous().to(cuda), ops.pack_deconv_weight(w, _lib.DZ_TF32).to(cuda), (2, cin, cout), scale.to(cuda),
+                 shift.to(cuda), True, out=out, out_coff=coff, mode=_lib.DZ_TF32)
+    assert util.rel_err(out[..., coff:coff + cout].permute(0, 3, 1, 2).cpu(), ref) < 2e-3
+    assert torch.all(out[..., :coff] == -3.0) and torch.all(out[..., coff + cout:] == -3.0)
+
+
 def test_sparse_to_bev(cuda):
     from detzero_b200.spconv.pytorch import SparseConvTensor
     shape, B = [2, 24, 24], 2
