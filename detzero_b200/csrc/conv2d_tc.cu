@@ -576,6 +576,193 @@ k_conv2d_tf32_halo_pair(const __grid_constant__ CUtensorMap tmA, const __grid_co
     conv2d_halo_body<BN, 1>(tmA, tmB, tmO, p, tiles_x, tiles_y, tiles_total);
 }
 
+// ---- persistent halo kernel: ONE CTA per SM walks the (patch, Cout block) list.  The non-persistent kernel above spends ~40 % of a CTA's
+// life outside the main loop on the short layers (128 -> 128: 144 MMAs = 9.2 K clk per patch; fused head stage 1, 64 -> 384: 72 MMAs):
+// barrier set-up, TMEM allocation, the first halo's L2 latency, the epilogue.  Here the TMEM accumulator is double-buffered (2 x BN columns):
+// the epilogue warps drain patch i while the MMA thread is already on patch i+1, the TMA producer runs ahead across patch boundaries, and
+// set-up is paid once per SM.  Epilogue staging has its own 4 KB per warp (the pipeline buffers never go idle).
+template <int BN>
+struct HpCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STG_BYTES = 8 * 4096;                                   // 8 epilogue warps x (32 rows x 128 B)
+    static constexpr int BUDGET = 200 * 1024;
+    static constexpr int B_STAGES = (BUDGET - HL_A_STAGES * HL_A_SLOT - STG_BYTES) / B_BYTES > 9 ? 9 : (BUDGET - HL_A_STAGES * HL_A_SLOT - STG_BYTES) / B_BYTES;
+    static constexpr int BUF = HL_A_STAGES * HL_A_SLOT + B_STAGES * B_BYTES + STG_BYTES;
+    static constexpr int SMEM = BUF + 1024 + 256;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;                           // warps that read the accumulator (BN = 32: one 32-column chunk)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+k_conv2d_tf32_halo_persist(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                           Conv2dParams p, int tiles_x, int tiles_y, int nblocks, int items) {
+    using Cfg = HpCfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smB = smem + HL_A_STAGES * HL_A_SLOT;
+    unsigned char* smS = smB + Cfg::B_STAGES * Cfg::B_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::BUF);
+    uint64_t* a_empty = a_full + HL_A_STAGES;
+    uint64_t* b_full = a_empty + HL_A_STAGES;
+    uint64_t* b_empty = b_full + Cfg::B_STAGES;
+    uint64_t* acc_full = b_empty + Cfg::B_STAGES;      // [2]
+    uint64_t* acc_empty = acc_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cchunks = p.cin / CT_BK;
+    const int G = gridDim.x;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        tc::prefetch_tmap(&tmO);
+        for (int s = 0; s < HL_A_STAGES; ++s) { tc::mbar_init(a_full + s, 1); tc::mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < Cfg::B_STAGES; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(acc_full + s, 1); tc::mbar_init(acc_empty + s, Cfg::EPI_WARPS); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item w -> (patch, Cout block): the Cout blocks of one patch are consecutive items, i.e. run at the same time on neighbouring
+    // SMs and share the patch's halo through L2
+    auto decode = [&](int w, int& tx0, int& ty0, int& b, int& n0) {
+        const int nb = w % nblocks;
+        int mt = w / nblocks;
+        tx0 = (mt % tiles_x) * HL_TW; mt /= tiles_x;
+        ty0 = (mt % tiles_y) * HL_TH;
+        b = mt / tiles_y;
+        n0 = nb * BN;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ait = 0, bit = 0;
+            for (int w = blockIdx.x; w < items; w += G) {
+                int tx0, ty0, b, n0;
+                decode(w, tx0, ty0, b, n0);
+                for (int cc = 0; cc < cchunks; ++cc, ++ait) {
+                    const int a = ait % HL_A_STAGES;
+                    tc::mbar_wait(a_empty + a, ((ait / HL_A_STAGES) & 1) ^ 1);
+                    tc::mbar_arrive_expect_tx(a_full + a, HL_A_BYTES);
+                    tc::tma_load_4d(smem + a * HL_A_SLOT, &tmA, a_full + a, cc * CT_BK, tx0 - p.pad, ty0 - p.pad, b);
+                    for (int tap = 0; tap < 9; ++tap, ++bit) {
+                        const int s = bit % Cfg::B_STAGES;
+                        tc::mbar_wait(b_empty + s, ((bit / Cfg::B_STAGES) & 1) ^ 1);
+                        tc::mbar_arrive_expect_tx(b_full + s, Cfg::B_BYTES);
+                        tc::tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, b_full + s, tap * p.cin + cc * CT_BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::instr_desc(2, 128, BN);
+            int ait = 0, bit = 0, i = 0;
+            for (int w = blockIdx.x; w < items; w += G, ++i) {
+                const int buf = i & 1;
+                tc::mbar_wait(acc_empty + buf, ((i >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator (item i-2)
+                tc::tcgen05_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                for (int cc = 0; cc < cchunks; ++cc, ++ait) {
+                    const int a = ait % HL_A_STAGES;
+                    tc::mbar_wait(a_full + a, (ait / HL_A_STAGES) & 1);
+                    const uint32_t ha = tc::smem_u32(smem + a * HL_A_SLOT);
+                    for (int tap = 0; tap < 9; ++tap, ++bit) {
+                        const int s = bit % Cfg::B_STAGES;
+                        tc::mbar_wait(b_full + s, (bit / Cfg::B_STAGES) & 1);
+                        tc::tcgen05_fence_after();
+                        const int r = tap / 3, sx = tap - r * 3;
+                        const uint32_t a0 = ha + (uint32_t)((r * HL_PITCH + sx) * 128);
+                        const uint64_t adesc = (uint64_t)((a0 >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((HL_PITCH * 128) >> 4) << 32) |
+                                               ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                        const uint64_t bdesc = tc::smem_desc_sw128(tc::smem_u32(smB + s * Cfg::B_BYTES));
+#pragma unroll
+                        for (int k = 0; k < CT_BK / 8; ++k)
+                            tc::mma_tf32(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cc | tap | k) ? 1u : 0u);
+                        tc::mma_commit(b_empty + s);
+                    }
+                    tc::mma_commit(a_empty + a);
+                }
+                tc::mma_commit(acc_full + buf);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int PER = BN >= 64 ? BN / 2 : BN;
+        if (!(half == 1 && BN < 64)) {
+            unsigned char* stg = smS + (warp - 2) * 4096;                          // this warp's own 32 rows x 128 B
+            const uint32_t stg_u = tc::smem_u32(stg) + (uint32_t)((lane >> 3) * 1024 + (lane & 7) * 128);
+            int i = 0;
+            for (int w = blockIdx.x; w < items; w += G, ++i) {
+                int tx0, ty0, b, n0;
+                decode(w, tx0, ty0, b, n0);
+                const int buf = i & 1;
+                tc::mbar_wait(acc_full + buf, (i >> 1) & 1);
+                tc::tcgen05_fence_after();
+#pragma unroll 1
+                for (int mc = half * PER; mc < half * PER + PER; mc += 32) {
+                    float v[32];
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + mc), v);
+                    if (mc + 32 >= half * PER + PER) {                             // last read of this accumulator by this warp: hand it back
+                        tc::tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(acc_empty + buf);
+                    }
+                    if (lane == 0) tc::tma_store_wait_read();                      // the previous store has read the staging rows
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int n = n0 + mc + j;
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (n < p.cout) {
+                            if (p.scale) { float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n)); o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+                            if (p.shift) { float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n)); o.x += sh.x; o.y += sh.y; o.z += sh.z; o.w += sh.w; }
+                        }
+                        if (p.relu) {
+                            o.x = tc::rna_tf32(fmaxf(o.x, 0.f)); o.y = tc::rna_tf32(fmaxf(o.y, 0.f));
+                            o.z = tc::rna_tf32(fmaxf(o.z, 0.f)); o.w = tc::rna_tf32(fmaxf(o.w, 0.f));
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u + (uint32_t)((((j >> 2) ^ (lane & 7))) << 4)),
+                                     "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                    }
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && n0 + mc < p.cout) {
+                        tc::tma_store_4d(&tmO, stg, p.out_coff + n0 + mc, tx0, ty0 + q * 4, b);
+                        tc::tma_store_commit();
+                    }
+                }
+            }
+            if (lane == 0) tc::tma_store_wait_read();
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+static int launch_halo_persist(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, int tiles_x, int tiles_y,
+                               cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        DZ_CUDA(cudaFuncSetAttribute(k_conv2d_tf32_halo_persist<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HpCfg<BN>::SMEM));
+        configured = true;
+    }
+    const int nblocks = dz_cdiv(p.cout, BN), items = tiles_x * tiles_y * p.B * nblocks;
+    const int grid = items < DZ_NUM_SMS ? items : DZ_NUM_SMS;
+    k_conv2d_tf32_halo_persist<BN><<<grid, CT_THREADS, HpCfg<BN>::SMEM, st>>>(tmA, tmB, tmO, p, tiles_x, tiles_y, nblocks, items);
+    DZ_LAUNCH_CHECK();
+    return DZ_OK;
+}
+
 template <int BN>
 static int launch_halo_single(const Conv2dParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, int tiles_x, int tiles_y,
                               cudaStream_t st) {
@@ -643,6 +830,15 @@ static int launch_halo(const Conv2dParams& p, int mode, cudaStream_t st) {
     const int tiles_x = dz_cdiv(p.Wo, HL_TW), tiles_y = dz_cdiv(p.Ho, HL_TH);
     if (pair) return bn == 256 ? launch_halo_pair<256>(p, tmA, tmB, tmO, tiles_x, tiles_y, st)
                      : (bn == 64 ? launch_halo_pair<64>(p, tmA, tmB, tmO, tiles_x, tiles_y, st) : launch_halo_pair<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st));
+    // DZ_CONV2D_PERSIST: 1 = persistent kernel (double-buffered TMEM accumulator) for the single-CTA shapes, 0 = one CTA per patch
+    static const int persist = getenv("DZ_CONV2D_PERSIST") ? atoi(getenv("DZ_CONV2D_PERSIST")) : 0;
+    if (persist) {
+        switch (bn) {
+            case 128: return launch_halo_persist<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+            case 64: return launch_halo_persist<64>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+            default: return launch_halo_persist<32>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
+        }
+    }
     switch (bn) {
         case 128: return launch_halo_single<128>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
         case 64: return launch_halo_single<64>(p, tmA, tmB, tmO, tiles_x, tiles_y, st);
