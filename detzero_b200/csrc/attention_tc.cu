@@ -360,13 +360,13 @@ k_attention_tf32_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* k_empty = bars + 3;     // [2]
     uint64_t* v_full = bars + 5;      // [2]
     uint64_t* v_empty = bars + 7;     // [2]
-    uint64_t* s_full = bars + 9;      // [2]
-    uint64_t* s_empty = bars + 11;    // [2]
-    uint64_t* p_full = bars + 13;     // [2]
-    uint64_t* p_empty = bars + 15;    // [2]
-    uint64_t* o_full = bars + 17;     // [2]
-    uint64_t* o_empty = bars + 19;    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint64_t* s_full = bars + 9;      // [3]: the score tiles run TWO key blocks ahead of the softmax (3 TMEM buffers), so S(j+1) never waits
+    uint64_t* s_empty = bars + 12;    // [3]  behind P(j-1) V(j-1) in the tensor pipe when the softmax asks for it
+    uint64_t* p_full = bars + 15;     // [2]
+    uint64_t* p_empty = bars + 17;    // [2]
+    uint64_t* o_full = bars + 19;     // [2]
+    uint64_t* o_empty = bars + 21;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr = TRACE && blockIdx.x == 0 && blockIdx.y == 0;
@@ -384,10 +384,10 @@ k_attention_tf32_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1);
             tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1);
-            tc::mbar_init(s_full + i, 1); tc::mbar_init(s_empty + i, AT_SM_WARPS);
             tc::mbar_init(p_full + i, AT_SM_WARPS); tc::mbar_init(p_empty + i, 1);
             tc::mbar_init(o_full + i, 1); tc::mbar_init(o_empty + i, AT_SM_WARPS);
         }
+        for (int i = 0; i < 3; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(s_empty + i, AT_SM_WARPS); }
         tc::fence_barrier_init();
     }
     if (warp == AT_SM_WARPS + 1) tc::tmem_alloc<512>(tmem_slot);
@@ -395,8 +395,7 @@ k_attention_tf32_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_s[2] = {tmem, tmem + 128};
-    const uint32_t tmem_ob[2] = {tmem + 256, tmem + 288};
+    const uint32_t tmem_ob[2] = {tmem + 384, tmem + 416};       // score tiles: columns [0, 384), block products: [384, 448)
 
     // register file: 640 threads x 96 at launch; the service warpgroup keeps 32 per thread and the softmax warpgroups take 112
     // register file: 640 threads x 96 at launch; the service warpgroup (warps 16-19) keeps 32 per thread, the softmax warpgroups take 112
@@ -406,14 +405,19 @@ k_attention_tf32_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) {
             tc::mbar_arrive_expect_tx(q_full, AT_TILE);
             tc::tma_load_2d(smem + At2Smem::Q, &tmQ, q_full, q_col0 + h * AT_D, b * Pq + q0);
-            for (int j = 0; j < nblk; ++j) {
-                const int st = j & 1;
-                AT2_T(0, tc::mbar_wait(k_empty + st, ((j >> 1) & 1) ^ 1));
-                tc::mbar_arrive_expect_tx(k_full + st, AT_TILE);
-                tc::tma_load_2d(smem + At2Smem::K + st * AT_TILE, &tmK, k_full + st, k_col0 + h * AT_D, b * Pk + j * AT_N);
-                AT2_T(1, tc::mbar_wait(v_empty + st, ((j >> 1) & 1) ^ 1));
-                tc::mbar_arrive_expect_tx(v_full + st, AT_TILE);
-                tc::tma_load_2d(smem + At2Smem::VT + st * AT_TILE, &tmV, v_full + st, v_col0 + h * AT_D, b * Pk + j * AT_N);
+            for (int t = 0; t <= nblk; ++t) {                       // K_t is requested before V_{t-1}: the score tiles run ahead of the products
+                if (t < nblk) {
+                    const int st = t & 1;
+                    AT2_T(0, tc::mbar_wait(k_empty + st, ((t >> 1) & 1) ^ 1));
+                    tc::mbar_arrive_expect_tx(k_full + st, AT_TILE);
+                    tc::tma_load_2d(smem + At2Smem::K + st * AT_TILE, &tmK, k_full + st, k_col0 + h * AT_D, b * Pk + t * AT_N);
+                }
+                if (t >= 1) {
+                    const int j = t - 1, st = j & 1;
+                    AT2_T(1, tc::mbar_wait(v_empty + st, ((j >> 1) & 1) ^ 1));
+                    tc::mbar_arrive_expect_tx(v_full + st, AT_TILE);
+                    tc::tma_load_2d(smem + At2Smem::VT + st * AT_TILE, &tmV, v_full + st, v_col0 + h * AT_D, b * Pk + j * AT_N);
+                }
             }
             if (tr) { g_at_trace[0] = acc[0]; g_at_trace[1] = acc[1]; g_at_trace[2] = 0; g_at_trace[3] = (unsigned)clock() - t_start; }
         }
@@ -425,19 +429,20 @@ k_attention_tf32_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint64_t qdesc = tc::smem_desc_sw128(tc::smem_u32(smem + At2Smem::Q));
             tc::mbar_wait(q_full, 0);
             auto issue_s = [&](int it) {                            // S[it&1] = Q K_it^T
-                const int st = it & 1;
+                const int st = it & 1, s3 = it % 3;
                 AT2_T(0, tc::mbar_wait(k_full + st, (it >> 1) & 1));
-                AT2_T(1, tc::mbar_wait(s_empty + st, ((it >> 1) & 1) ^ 1));
+                AT2_T(1, tc::mbar_wait(s_empty + s3, ((it / 3) & 1) ^ 1));
                 tc::tcgen05_fence_after();
                 const uint64_t kdesc = tc::smem_desc_sw128(tc::smem_u32(smem + At2Smem::K + st * AT_TILE));
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) tc::mma_tf32(tmem_s[st], qdesc + (uint64_t)(kk * 2), kdesc + (uint64_t)(kk * 2), idesc_s, kk ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk) tc::mma_tf32(tmem + (uint32_t)(s3 * 128), qdesc + (uint64_t)(kk * 2), kdesc + (uint64_t)(kk * 2), idesc_s, kk ? 1u : 0u);
                 tc::mma_commit(k_empty + st);
-                tc::mma_commit(s_full + st);
+                tc::mma_commit(s_full + s3);
             };
             issue_s(0);
+            if (nblk > 1) issue_s(1);
             for (int j = 0; j < nblk; ++j) {
-                if (j + 1 < nblk) issue_s(j + 1);                   // S of the next block overlaps this block's softmax
+                if (j + 2 < nblk) issue_s(j + 2);                   // two blocks ahead: queued in front of P_j V_j, ready long before the softmax wants it
                 const int st = j & 1;
                 AT2_T(2, tc::mbar_wait(v_full + st, (j >> 1) & 1));
                 AT2_T(3, tc::mbar_wait(p_full + st, (j >> 1) & 1));
@@ -479,28 +484,28 @@ k_attention_tf32_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // (the four warps of an SM sub-partition are the four column groups of one row quarter and run in lockstep through the row-max
         // exchange, so nothing else would hide that latency there).  sa / sb alternate as "this block" / "next block".
         auto issue_half = [&](int jn, int half, float (&dst)[32]) {     // 16 of the thread's 32 score columns of block jn: TMEM -> registers, not waited for
-            const int sn = jn & 1;
-            if (half == 0) { AT2_T(0, tc::mbar_wait(s_full + sn, (jn >> 1) & 1)); }
+            const int sn = jn % 3;
+            if (half == 0) { AT2_T(0, tc::mbar_wait(s_full + sn, (jn / 3) & 1)); }
             tc::tcgen05_fence_after();
             uint32_t* r = reinterpret_cast<uint32_t*>(dst) + half * 16;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
                            "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                         : "r"(tmem_s[sn] + lane_base + (uint32_t)(c0 + half * 16)));
+                         : "r"(tmem + (uint32_t)(sn * 128) + lane_base + (uint32_t)(c0 + half * 16)));
         };
-        auto mask_byte = [&](int jn) {
-            const int mkey = jn * AT_N + c0 + lane;                 // lane-parallel mask read: one byte per lane, 32 keys per warp
-            return mkey >= Pk || (mrow && __ldg(mrow + mkey));
+        auto mask_byte = [&](int jn) -> unsigned {                   // lane-parallel mask read: one byte per lane, 32 keys per warp; the RAW byte is kept
+            const int mkey = jn * AT_N + c0 + lane;                 // in a register and only tested at the ballot one block later (load latency hidden)
+            return mkey >= Pk ? 1u : (mrow ? (unsigned)__ldg(mrow + mkey) : 0u);
         };
-        bool mk_next = mask_byte(0);
+        unsigned mk_next = mask_byte(0);
         auto block = [&](int j, float (&sc)[32], float (&scn)[32]) {
             const int st = j & 1;
             const unsigned tb0 = tr ? (unsigned)clock() : 0u;
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");          // S_j (issued one block ago) is in sc
             tc::tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(s_empty + st);           // the scores are in registers: the tensor core may overwrite S[st]
-            const uint32_t mb = __ballot_sync(0xffffffffu, mk_next); // bit c = key c of this thread's 32-key column group is masked
+            if (lane == 0) tc::mbar_arrive(s_empty + j % 3);        // the scores are in registers: the tensor core may overwrite this S buffer
+            const uint32_t mb = __ballot_sync(0xffffffffu, mk_next != 0u); // bit c = key c of this thread's 32-key column group is masked
             float lm = -INFINITY;
             if (mb == 0u) {
 #pragma unroll
