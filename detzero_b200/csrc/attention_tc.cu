@@ -4,20 +4,20 @@
 // (refining/detzero_refine/models/modules/transformer/multi_head_attention.py:266-286), head_dim 32, without ever
 // materialising the (B*H, Pq, Pk) score tensor (15.7 GB at the BASELINE config-4 size).
 //
-// One CTA = one (batch, head) x one tile of 128 queries.  TWO passes over the keys instead of the usual online-softmax
-// rescaling: pass 1 computes S = Q K^T block by block on the tensor cores and only tracks the row maxima; pass 2 recomputes
-// S, forms P = exp(S - max) and accumulates O += P V in TMEM.  With head_dim 32 the QK^T MMAs are 4 of the 20 MMAs per
-// key block, so recomputing them costs 25 % more tensor work and removes the accumulator-correction path entirely.
-//   warps 4-7: loaders -- warp 4 lane 0: TMA for the Q tile and the K blocks (rows of 128 B = one head slice, SWIZZLE_128B =
-//             K-major UMMA operand); all four: register transpose of one 32-key k-block of V each into V^T (the B operand of
-//             P V must be K-major in keys).  One warp doing all four k-blocks was the bottleneck of round 1's kernel: its
-//             32 L2-latency-exposed row loads + 128 scalar shared stores per lane took ~5 K clk per 128-key block
-//   warp 8  : single-thread MMA issuer (S = Q K^T : M128 N128 K32 ; O += P V^T : M128 N32 K128)
+// One CTA = one (batch, head) x one tile of 128 queries.  Two kernels live here:
+//   * k_attention_tf32_v2 (default): SINGLE pass over the keys, online softmax with the block products P_j V_j folded into a register
+//     accumulator -- see the block comment above it (V as an MN-major TMA tile, score tiles two blocks ahead in three TMEM buffers,
+//     setmaxnreg).  291 us on the PRM cross-attention shape (16 tracks x 200 queries x 9600 keys x 8 heads).
+//   * k_attention_tf32 (DZ_ATTN_TWO_PASS=1, kept for A/B): TWO passes over the keys instead of the online-softmax rescaling: pass 1
+//     computes S = Q K^T block by block on the tensor cores and only tracks the row maxima; pass 2 recomputes S, forms
+//     P = exp(S - max) and accumulates O += P V in TMEM (528 us on the same shape).  Its roles:
+//   warps 16-19: loaders -- warp 16 lane 0: TMA for the Q tile and the K blocks (rows of 128 B = one head slice, SWIZZLE_128B =
+//             K-major UMMA operand); all four: register transpose of one 32-key k-block of V each into V^T
+//   warp 20 : single-thread MMA issuer (S = Q K^T : M128 N128 K32 ; O += P V^T : M128 N32 K128)
 //   warps 0-15: softmax.  Thread = (query row, 32-key column group): tcgen05.ld of its 32 scores, masking, max / exp / sum, P
 //             written to shared memory in the swizzled A-operand layout; the four column groups of a row combine their maxima
 //             after pass 1 and their sums at the end through shared memory.  (Round 1 used ONE thread per row, 128 scores each:
 //             the clock trace showed those 4 warps busy 817 K of the CTA's 870 K clocks while the MMA thread waited for P.)
-// S is double-buffered in TMEM so S(j+1) is computed while the softmax of block j runs.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc.cuh"
@@ -320,12 +320,18 @@ k_attention_tf32(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // =====================================================================================================================
 // v2: SINGLE pass over the keys (online softmax).  The two-pass kernel above reads every 128 x 128 score tile from TMEM twice, and
-// tcgen05.ld moves 64 B/clk: 2 x 1024 clk per key block before any arithmetic (tools/trace_attention.py).  Here S_j is read once;
-// the running row maximum is combined across a row's four column-group threads through shared memory (one 512-thread named
-// barrier per block); P_j = exp2(S_j - m_j) goes to shared memory as before; the tensor core computes the BLOCK product
-// Oblk_j = P_j V_j into a double-buffered 32-column TMEM tile (accumulate only inside the block), and the row's owner thread folds it
-// into a REGISTER accumulator one block later: O <- O * exp2(m_{j-2} - m_{j-1}) + Oblk_{j-1}.  No accumulator rescaling in TMEM, no
-// tcgen05.st, no dependency of PV(j+1) on a correction of PV(j).
+// tcgen05.ld moves 64 B/clk: 2 x 1024 clk per key block before any arithmetic (tools/trace_attention.py).  Here:
+//   * S_j is read once (half-by-half, issued under the exp2 phase of block j-1); the running row maximum is combined across a row's four
+//     column-group threads through shared memory + ONE 128-thread named barrier per row quarter and block;
+//   * P_j = exp2(S_j - m_j) goes to shared memory (SW128 A operand); the tensor core computes the BLOCK product Oblk_j = P_j V_j into a
+//     double-buffered 32-column TMEM tile (accumulate only inside the block) and each of the row's four threads folds its 8 output
+//     dims into a REGISTER accumulator one block later: O <- O * exp2(m_{j-2} - m_{j-1}) + Oblk_{j-1}.  No accumulator rescaling in
+//     TMEM, no tcgen05.st, no dependency of PV(j+1) on a correction of PV(j);
+//   * V_j is the TMA tile itself ([key][32 dims], rows of 128 B) used as an MN-major B operand -- no transposed copy (for tf32 that needs
+//     descriptor layout type 1 "128B swizzle, 32B atoms" and CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+//   * the score tiles run TWO blocks ahead of the softmax in three 128-column TMEM buffers (the ncu source page showed 15 % of the stall
+//     samples on s_full when S(j+1) queued behind P(j-1) V(j-1)); K_t is requested before V_{t-1};
+//   * 20 warps: 16 softmax (setmaxnreg.inc 112), TMA producer, MMA issuer, 2 idle (the service warpgroup does setmaxnreg.dec 32).
 // =====================================================================================================================
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
